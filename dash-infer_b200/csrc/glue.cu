@@ -1,0 +1,218 @@
+// b200spark — glue ops of the decode graph ("next" rows): RMSNorm, rotary, binary,
+// embedding lookup, greedy argmax, device-resident sequence lengths.  All bandwidth-trivial at decode;
+// they exist so that a whole decode step runs without leaving the library (and the CUDA graph).
+// Reference counterparts: csrc/core/kernel/cuda/layernorm.cu:86 (LayerNormNoBeta), rotary.cu:23,
+// binary.cu, embedding.cu, and GenerateOp with top_k=1 (generate_impl_cpu.hpp:153-165 = argmax).
+#include "b2_common.cuh"
+
+namespace b2 {
+
+__global__ void __launch_bounds__(256) rmsnorm_kernel(__nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ x,
+                                                      const __nv_bfloat16* __restrict__ gamma, int cols, float eps) {
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ float red[8];
+  const int row = blockIdx.x;
+  const __nv_bfloat16* xr = x + (size_t)row * cols;
+  float ss = 0.f;
+  for (int i = threadIdx.x * 8; i < cols; i += 256 * 8) {
+    const uint4 v = *reinterpret_cast<const uint4*>(xr + i);
+    const float f[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y), bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  const float inv = rsqrtf(tot / (float)cols + eps);
+  for (int i = threadIdx.x * 8; i < cols; i += 256 * 8) {
+    const uint4 v = *reinterpret_cast<const uint4*>(xr + i);
+    const uint4 gv = *reinterpret_cast<const uint4*>(gamma + i);
+    uint4 o;
+    o.x = pack_bf16x2(bf16_lo(v.x) * inv * bf16_lo(gv.x), bf16_hi(v.x) * inv * bf16_hi(gv.x));
+    o.y = pack_bf16x2(bf16_lo(v.y) * inv * bf16_lo(gv.y), bf16_hi(v.y) * inv * bf16_hi(gv.y));
+    o.z = pack_bf16x2(bf16_lo(v.z) * inv * bf16_lo(gv.z), bf16_hi(v.z) * inv * bf16_hi(gv.z));
+    o.w = pack_bf16x2(bf16_lo(v.w) * inv * bf16_lo(gv.w), bf16_hi(v.w) * inv * bf16_hi(gv.w));
+    *reinterpret_cast<uint4*>(y + (size_t)row * cols + i) = o;
+  }
+}
+
+// in-place NeoX rotary on the q and k heads: one warp per (sequence, head)
+__global__ void __launch_bounds__(128) rotary_kernel(__nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ pos, int batch,
+                                                     int n_heads, int n_groups, int rotary_dim, float log2_base) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31;
+  const int rot_heads = n_heads + n_groups;
+  const int slots = n_heads + 2 * n_groups;
+  const int wid = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (wid >= batch * rot_heads) return;
+  const int b = wid / rot_heads, h = wid - b * rot_heads;
+  __nv_bfloat16* ptr = qkv + ((size_t)b * slots + h) * 128 + lane * 4;
+  const uint2 raw = *reinterpret_cast<const uint2*>(ptr);
+  float x[4] = {bf16_lo(raw.x), bf16_hi(raw.x), bf16_lo(raw.y), bf16_hi(raw.y)};
+  const int half = rotary_dim >> 1;
+  float other[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) other[i] = __shfl_xor_sync(0xffffffffu, x[i], half == 64 ? 16 : 8);
+  const int ps = pos[b];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int d = lane * 4 + i;
+    if (d < rotary_dim) {
+      const int fi = d % half;
+      const float inv = exp2f(-log2_base * (2.0f * fi / (float)rotary_dim));
+      float sn, cs;
+      sincosf((float)ps * inv, &sn, &cs);
+      x[i] = d < half ? x[i] * cs - other[i] * sn : x[i] * cs + other[i] * sn;
+    }
+  }
+  *reinterpret_cast<uint2*>(ptr) = make_uint2(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]));
+}
+
+__global__ void __launch_bounds__(256) binary_kernel(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ a,
+                                                     const __nv_bfloat16* __restrict__ b, int64_t n, int op) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    const uint4 va = *reinterpret_cast<const uint4*>(a + i), vb = *reinterpret_cast<const uint4*>(b + i);
+    const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+    uint32_t wo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float l = op == B2_BIN_ADD ? bf16_lo(wa[j]) + bf16_lo(wb[j]) : bf16_lo(wa[j]) * bf16_lo(wb[j]);
+      const float h = op == B2_BIN_ADD ? bf16_hi(wa[j]) + bf16_hi(wb[j]) : bf16_hi(wa[j]) * bf16_hi(wb[j]);
+      wo[j] = pack_bf16x2(l, h);
+    }
+    *reinterpret_cast<uint4*>(out + i) = make_uint4(wo[0], wo[1], wo[2], wo[3]);
+  } else {
+    for (int64_t j = i; j < n; ++j) {
+      const float x = __bfloat162float(a[j]), y = __bfloat162float(b[j]);
+      out[j] = __float2bfloat16(op == B2_BIN_ADD ? x + y : x * y);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) embedding_kernel(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ table,
+                                                        const int64_t* __restrict__ ids, int hidden) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int b = blockIdx.x;
+  const int64_t id = ids[b];
+  for (int i = threadIdx.x * 8; i < hidden; i += 128 * 8)
+    *reinterpret_cast<uint4*>(out + (size_t)b * hidden + i) = *reinterpret_cast<const uint4*>(table + (size_t)id * hidden + i);
+}
+
+// greedy sampling: lowest index among the maxima (bit-exact index contract)
+__global__ void __launch_bounds__(1024) argmax_kernel(int64_t* __restrict__ ids_out, const __nv_bfloat16* __restrict__ logits, int n,
+                                                      int64_t ld) {
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ float sv[32];
+  __shared__ int si[32];
+  const int b = blockIdx.x;
+  const __nv_bfloat16* row = logits + (size_t)b * ld;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < n; i += 1024) {
+    const float v = __bfloat162float(row[i]);
+    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    best = sv[threadIdx.x];
+    bi = si[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (threadIdx.x == 0) ids_out[b] = bi;
+  }
+}
+
+__global__ void lens_add_kernel(int32_t* lens, int batch, int delta) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < batch) lens[i] += delta;
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+#define B2_LAUNCH_CHECK(name, call)            \
+  do {                                         \
+    cudaError_t _e = (call);                   \
+    if (_e != cudaSuccess) {                   \
+      set_last_error(name, _e);                \
+      return B2_ERR_CUDA;                      \
+    }                                          \
+  } while (0)
+
+extern "C" {
+
+int b2_rmsnorm(void* y, const void* x, const void* gamma, int rows, int cols, float eps, void* stream) {
+  if (!y || !x || !gamma || rows <= 0 || cols <= 0) return B2_ERR_PARAM;
+  if (cols % 8) return B2_ERR_UNSUPPORTED;
+  B2_LAUNCH_CHECK("rmsnorm", launch(rmsnorm_kernel, dim3(rows), dim3(256), 0, (cudaStream_t)stream, true, (__nv_bfloat16*)y,
+                                    (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma, cols, eps));
+  return B2_OK;
+}
+
+int b2_rotary(void* qkv, const int32_t* pos, int batch, int n_heads, int n_groups, int head_size, const b2_rope_cfg* rope,
+              void* stream) {
+  if (!qkv || !pos || !rope || batch <= 0) return B2_ERR_PARAM;
+  if (head_size != 128 || (rope->rotary_dim != 128 && rope->rotary_dim != 64)) return B2_ERR_UNSUPPORTED;
+  const int warps = batch * (n_heads + n_groups);
+  B2_LAUNCH_CHECK("rotary", launch(rotary_kernel, dim3((warps + 3) / 4), dim3(128), 0, (cudaStream_t)stream, true,
+                                   (__nv_bfloat16*)qkv, pos, batch, n_heads, n_groups, rope->rotary_dim, log2f(rope->base)));
+  return B2_OK;
+}
+
+int b2_binary(void* out, const void* a, const void* b, int64_t n, int op, void* stream) {
+  if (!out || !a || !b || n <= 0) return B2_ERR_PARAM;
+  if (op != B2_BIN_ADD && op != B2_BIN_MUL) return B2_ERR_UNSUPPORTED;
+  const int64_t blocks = (n + 2047) / 2048;
+  B2_LAUNCH_CHECK("binary", launch(binary_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, true,
+                                   (__nv_bfloat16*)out, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, n, op));
+  return B2_OK;
+}
+
+int b2_embedding(void* out, const void* table, const int64_t* ids, int batch, int hidden, void* stream) {
+  if (!out || !table || !ids || batch <= 0 || hidden <= 0) return B2_ERR_PARAM;
+  if (hidden % 8) return B2_ERR_UNSUPPORTED;
+  B2_LAUNCH_CHECK("embedding", launch(embedding_kernel, dim3(batch), dim3(128), 0, (cudaStream_t)stream, true, (__nv_bfloat16*)out,
+                                      (const __nv_bfloat16*)table, ids, hidden));
+  return B2_OK;
+}
+
+int b2_argmax(int64_t* ids_out, const void* logits, int batch, int n, int64_t ld, void* stream) {
+  if (!ids_out || !logits || batch <= 0 || n <= 0) return B2_ERR_PARAM;
+  B2_LAUNCH_CHECK("argmax", launch(argmax_kernel, dim3(batch), dim3(1024), 0, (cudaStream_t)stream, true, ids_out,
+                                   (const __nv_bfloat16*)logits, n, ld));
+  return B2_OK;
+}
+
+int b2_lens_add(int32_t* lens, int batch, int delta, void* stream) {
+  if (!lens || batch <= 0) return B2_ERR_PARAM;
+  B2_LAUNCH_CHECK("lens_add", launch(lens_add_kernel, dim3((batch + 127) / 128), dim3(128), 0, (cudaStream_t)stream, true, lens,
+                                     batch, delta));
+  return B2_OK;
+}
+
+}  // extern "C"

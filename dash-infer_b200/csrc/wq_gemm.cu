@@ -1,0 +1,718 @@
+// b200spark — weight-only quantized GEMV/GEMM for the decode step (small M), sm_100a.
+//
+// Replaces the reference's K1/K2/K3/K6/K7/K8 kernels and the dequant+cuBLAS fallbacks
+// (csrc/core/kernel/cuda/gemm_lowp/gemm_a16w4_{perc,subc}_kernel.cu, gemm_a16w8_*_kernel.cu,
+//  gemm_lowp_utils.cuh:582-604 reduce_sum) with ONE weight-streaming kernel family:
+//
+//   * init time: the reference [K,N/2] nibble / [K,N] int8 / [K,N] bf16 weights are re-laid-out into
+//     tiles of (128 n x 64 k) such that each CTA's K-slice is ONE contiguous byte range and each
+//     lane's 16-byte shared-memory word is exactly the mma.m16n8k16 A-fragments it needs.
+//   * run time: a producer lane streams the CTA's slice HBM -> shared memory with TMA 1-D bulk copies
+//     (cp.async.bulk + mbarrier ring).  The producer does NOT wait for the previous kernel
+//     (programmatic dependent launch): weights of op i+1 stream in while op i drains.
+//   * 8 consumer warps (one n16 tile each) expand nibbles to exact bf16 integers (16+q) with
+//     lop3/shf only, run C^T[n16 x m8] += W^T[n16 x k16] * A^T[k16 x m8] on the tensor cores
+//     (weights = A operand, activations = B operand: batch 1..8 fills the n8 side, no wasted rows),
+//     and apply the affine dequant on the fp32 accumulators:  s * (acc - (16+z) * sum_k a).
+//   * split-K across CTAs with fp32 partials in the caller's workspace; the last CTA of an n-group
+//     (device counter) sums them in fixed order => deterministic, fused bias/activation/residual.
+//
+// Roofline: HBM-bound; algorithmic bytes/launch = K*N*wbits/8 + 4*G*N + 2*M*(K+N).
+#include <cstdio>
+#include <cstdlib>
+#include <new>
+
+#include "b2_common.cuh"
+
+namespace b2 {
+
+constexpr int kWarps = 8;                  // consumer warps per CTA
+constexpr int kThreads = kWarps * 32 + 32; // + producer warp
+constexpr int kBN = kWarps * 16;           // n per CTA
+constexpr int kBK = 64;                    // k per tile
+constexpr int kStageBytes = 8192;
+constexpr uint32_t kMask4 = 0x00780078u;   // nibble at mantissa bits 3..6 of each bf16 half
+constexpr uint32_t kMagic = 0x41804180u;   // bf16 16.0 in both halves: 16 + q exactly
+
+struct GemmParams {
+  const uint8_t* packed;
+  const float2* sz;  // [G][Np] (scale, zero + bias-constant)
+  const __nv_bfloat16* A;
+  int64_t lda;
+  __nv_bfloat16* C;
+  int64_t ldc;
+  const __nv_bfloat16* bias;
+  const __nv_bfloat16* residual;
+  float* ws;
+  unsigned* counters;
+  int M, N, K, Np, KT, NG, S;
+  int group_tiles;  // k-tiles per quant group (GROUPED) else 0
+  int quanta;       // number of split quanta (KT / max(group_tiles,1))
+  int xt;           // k-tiles per activation chunk
+  int nstage;
+  int act;
+  float alpha;
+};
+
+template <int WBITS>
+struct WTraits {
+  static constexpr int LB = WBITS == 4 ? 16 : (WBITS == 8 ? 32 : 64);  // bytes per lane per k-tile
+  static constexpr int NCH = LB / 16;                                   // 16B chunks per lane per k-tile
+  static constexpr int TILE_BYTES = kWarps * 32 * LB;                   // 4K / 8K / 16K
+  static constexpr int TPS = kStageBytes / TILE_BYTES > 0 ? kStageBytes / TILE_BYTES : 1;  // tiles per stage
+  static constexpr int STAGE_BYTES = TPS * TILE_BYTES;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+template <int WBITS, int MT, bool GROUPED>
+__global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
+  using T = WTraits<WBITS>;
+  constexpr int MP = 8 * MT;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+
+  const int ng = blockIdx.x / p.S;
+  const int s = blockIdx.x - ng * p.S;
+  const int gt = GROUPED ? p.group_tiles : 1;
+  const int q0 = (int)((int64_t)s * p.quanta / p.S), q1 = (int)((int64_t)(s + 1) * p.quanta / p.S);
+  const int kt0 = q0 * gt, kt1 = q1 * gt;
+  const int nt = kt1 - kt0;
+
+  // ---- shared memory carve-up
+  uint8_t* ring = smem;
+  const int ring_bytes = p.nstage * T::STAGE_BYTES;
+  const int XS = p.xt * 128 + 16;  // activation row stride (bytes), == 16 mod 128: conflict-free LDS.128
+  uint8_t* xs = ring + ring_bytes;
+  float* fs = reinterpret_cast<float*>(xs + MP * XS);        // [MP][kBN] partial tile
+  float* suma = fs + MP * kBN;                                // [MP][groups per chunk] (or [MP])
+  const int gpc = GROUPED ? p.xt / gt : 1;                    // groups per chunk
+  uint64_t* full = reinterpret_cast<uint64_t*>(suma + MP * (gpc > 0 ? gpc : 1) + 4);
+  full = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(full) + 7) & ~uintptr_t(7));
+  uint64_t* empty = full + p.nstage;
+  __shared__ int s_is_last;
+
+  if (tid == 0) {
+    for (int i = 0; i < p.nstage; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], kWarps);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_launch_dependents();  // let the next kernel start streaming ITS weights as soon as SM resources free up
+
+  const uint8_t* wsrc = p.packed + ((size_t)ng * p.KT + kt0) * T::TILE_BYTES;
+  const int nstages_total = (nt + T::TPS - 1) / T::TPS;
+
+  if (warp == kWarps) {
+    // ===================== producer: TMA bulk copies, independent of the previous kernel ==========
+    if (lane == 0) {
+      for (int i = 0; i < nstages_total; ++i) {
+        const int slot = i % p.nstage, use = i / p.nstage;
+        mbar_wait(&empty[slot], (use & 1) ^ 1);
+        const int tiles = min(T::TPS, nt - i * T::TPS);
+        const uint32_t bytes = tiles * T::TILE_BYTES;
+        mbar_arrive_expect_tx(&full[slot], bytes);
+        bulk_g2s(ring + slot * T::STAGE_BYTES, wsrc + (size_t)i * T::STAGE_BYTES, bytes, &full[slot]);
+      }
+    }
+    return;
+  }
+
+  // ===================== consumers =====================
+  const int n0 = ng * kBN + warp * 16 + g;  // this thread's two output channels: n0, n0+8
+  float2 sz0 = make_float2(1.f, 0.f), sz1 = make_float2(1.f, 0.f);
+  if (!GROUPED && WBITS != 16) {  // immutable after prepare: safe to read before the dependency wait
+    sz0 = p.sz[n0];
+    sz1 = p.sz[n0 + 8];
+  }
+
+  float acc[MT][4], acch[MT][4], facc[MT][4];
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[m][c] = acch[m][c] = facc[m][c] = 0.f;
+
+  pdl_wait();  // activations / workspace / counters belong to the previous kernels from here on
+
+  const uint32_t ring_u32 = smem_u32(ring);
+  const uint32_t xs_u32 = smem_u32(xs);
+  const int ctid = tid;  // 0..255 among consumers
+  int tile_i = 0;        // tile index within the unit
+
+  for (int xc0 = 0; xc0 < nt; xc0 += p.xt) {
+    const int xn = min(p.xt, nt - xc0);
+    named_bar_sync(1, kWarps * 32);  // previous chunk fully consumed
+    // ---- stage activations A[m][k-chunk] (bf16) -> xs, zero-filling m >= M and k >= K
+    {
+      const int vec_per_row = xn * 8;  // 16B vectors
+      const int64_t kbase = (int64_t)(kt0 + xc0) * kBK;
+      for (int idx = ctid; idx < MP * vec_per_row; idx += kWarps * 32) {
+        const int m = idx / vec_per_row, v = idx - m * vec_per_row;
+        const int64_t k = kbase + v * 8;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (m < p.M && k < p.K) val = *reinterpret_cast<const uint4*>(p.A + (int64_t)m * p.lda + k);
+        *reinterpret_cast<uint4*>(xs + m * XS + v * 16) = val;
+      }
+    }
+    named_bar_sync(1, kWarps * 32);
+    // ---- sum_k a[m][k] per (row, quant group) of this chunk — the zero-point term
+    {
+      const int ngroups = GROUPED ? xn / gt : 1;
+      const int vec_per_group = (GROUPED ? gt : xn) * 8;
+      for (int job = warp; job < MP * ngroups; job += kWarps) {
+        const int m = job / ngroups, gi = job - m * ngroups;
+        float sacc = 0.f;
+        for (int v = lane; v < vec_per_group; v += 32) {
+          const uint4 val = *reinterpret_cast<const uint4*>(xs + m * XS + (gi * vec_per_group + v) * 16);
+          sacc += bf16_lo(val.x) + bf16_hi(val.x) + bf16_lo(val.y) + bf16_hi(val.y) + bf16_lo(val.z) +
+                  bf16_hi(val.z) + bf16_lo(val.w) + bf16_hi(val.w);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+        if (lane == 0) {
+          if (GROUPED) suma[m * gpc + gi] = sacc;
+          else suma[m] = (xc0 == 0 ? 0.f : suma[m]) + sacc;
+        }
+      }
+    }
+    named_bar_sync(1, kWarps * 32);
+
+    // ---- main loop over the k-tiles of this chunk
+    for (int xt_i = 0; xt_i < xn; ++xt_i, ++tile_i) {
+      const int stage_i = tile_i / T::TPS, in_stage = tile_i - stage_i * T::TPS;
+      const int slot = stage_i % p.nstage, use = stage_i / p.nstage;
+      if (in_stage == 0) mbar_wait(&full[slot], use & 1);
+
+      if (GROUPED && (xt_i % gt) == 0) {  // prefetch this group's (scale, zero) — consumed at group end
+        const int grp = (kt0 + xc0 + xt_i) / gt;
+        sz0 = p.sz[(size_t)grp * p.Np + n0];
+        sz1 = p.sz[(size_t)grp * p.Np + n0 + 8];
+      }
+
+      // activation (B) fragments: this thread's 16 consecutive k of the tile, for each m8 block
+      uint4 xb[MT][2];
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const uint32_t a = xs_u32 + (m * 8 + g) * XS + xt_i * 128 + t * 32;
+        xb[m][0] = lds128(a);
+        xb[m][1] = lds128(a + 16);
+      }
+      const uint32_t wbase = ring_u32 + slot * T::STAGE_BYTES + in_stage * T::TILE_BYTES + warp * (32 * T::LB) + lane * 16;
+
+      if (WBITS == 4) {
+        const uint4 wv = lds128(wbase);
+        const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t w = ww[j];
+          const uint32_t a0 = lop3_and_or(w, kMask4, kMagic);
+          const uint32_t a1 = lop3_and_or(__funnelshift_r(w, w, 4), kMask4, kMagic);
+          const uint32_t a2 = lop3_and_or(__funnelshift_r(w, w, 8), kMask4, kMagic);
+          const uint32_t a3 = lop3_and_or(__funnelshift_r(w, w, 12), kMask4, kMagic);
+#pragma unroll
+          for (int m = 0; m < MT; ++m) {
+            const uint32_t b0 = (j & 1) ? ((j & 2) ? xb[m][1].z : xb[m][0].z) : ((j & 2) ? xb[m][1].x : xb[m][0].x);
+            const uint32_t b1 = (j & 1) ? ((j & 2) ? xb[m][1].w : xb[m][0].w) : ((j & 2) ? xb[m][1].y : xb[m][0].y);
+            mma_bf16_16816(acc[m], a0, a1, a2, a3, b0, b1);
+          }
+        }
+      } else if (WBITS == 8) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const uint4 wv = lds128(wbase + c * 512);
+          const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            const uint32_t wa = ww[2 * jj], wb = ww[2 * jj + 1];
+            const uint32_t l0 = lop3_and_or(wa, kMask4, kMagic);
+            const uint32_t h0 = lop3_and_or(__funnelshift_r(wa, wa, 4), kMask4, kMagic);
+            const uint32_t l1 = lop3_and_or(__funnelshift_r(wa, wa, 8), kMask4, kMagic);
+            const uint32_t h1 = lop3_and_or(__funnelshift_r(wa, wa, 12), kMask4, kMagic);
+            const uint32_t l2 = lop3_and_or(wb, kMask4, kMagic);
+            const uint32_t h2 = lop3_and_or(__funnelshift_r(wb, wb, 4), kMask4, kMagic);
+            const uint32_t l3 = lop3_and_or(__funnelshift_r(wb, wb, 8), kMask4, kMagic);
+            const uint32_t h3 = lop3_and_or(__funnelshift_r(wb, wb, 12), kMask4, kMagic);
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+              const uint32_t b0 = jj ? xb[m][c].z : xb[m][c].x;
+              const uint32_t b1 = jj ? xb[m][c].w : xb[m][c].y;
+              mma_bf16_16816(acc[m], l0, l1, l2, l3, b0, b1);
+              mma_bf16_16816(acch[m], h0, h1, h2, h3, b0, b1);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 wv = lds128(wbase + j * 512);
+#pragma unroll
+          for (int m = 0; m < MT; ++m) {
+            const uint32_t b0 = (j & 1) ? xb[m][j >> 1].z : xb[m][j >> 1].x;
+            const uint32_t b1 = (j & 1) ? xb[m][j >> 1].w : xb[m][j >> 1].y;
+            mma_bf16_16816(acc[m], wv.x, wv.y, wv.z, wv.w, b0, b1);
+          }
+        }
+      }
+
+      if (in_stage == T::TPS - 1 || tile_i == nt - 1) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);
+      }
+
+      if (GROUPED && ((xt_i + 1) % gt) == 0) {  // fold this quant group into the fp32 result
+        const int gi = xt_i / gt;
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float2 z = (c < 2) ? sz0 : sz1;
+            const float sa = suma[(m * 8 + 2 * t + (c & 1)) * gpc + gi];
+            const float raw = (WBITS == 8) ? (16.f * acch[m][c] + acc[m][c]) : acc[m][c];
+            facc[m][c] += z.x * (raw - z.y * sa);
+            acc[m][c] = 0.f;
+            acch[m][c] = 0.f;
+          }
+        }
+      }
+    }
+  }
+
+  // ---- dequant epilogue on the accumulators (per-channel) and park the tile in shared memory
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float v;
+      if (WBITS == 16) v = acc[m][c];
+      else if (GROUPED) v = facc[m][c];
+      else {
+        const float2 z = (c < 2) ? sz0 : sz1;
+        const float sa = suma[m * 8 + 2 * t + (c & 1)];
+        const float raw = (WBITS == 8) ? (16.f * acch[m][c] + acc[m][c]) : acc[m][c];
+        v = z.x * (raw - z.y * sa);
+      }
+      fs[(m * 8 + 2 * t + (c & 1)) * kBN + warp * 16 + g + (c >> 1) * 8] = v;
+    }
+  }
+  named_bar_sync(1, kWarps * 32);
+
+  const int MPK = MP * kBN;
+  if (p.S > 1) {
+    float* wsu = p.ws + ((size_t)ng * p.S + s) * MPK;
+    for (int i = ctid * 4; i < p.M * kBN; i += kWarps * 32 * 4)
+      *reinterpret_cast<float4*>(wsu + i) = *reinterpret_cast<const float4*>(fs + i);
+    __threadfence();
+    named_bar_sync(1, kWarps * 32);
+    if (ctid == 0) {
+      const unsigned prev = atomicAdd(&p.counters[ng], 1u);
+      s_is_last = (prev == (unsigned)(p.S - 1));
+    }
+    named_bar_sync(1, kWarps * 32);
+    if (!s_is_last) return;
+    __threadfence();
+    // fixed-order sum over the S partials (deterministic)
+    const float* wsg = p.ws + (size_t)ng * p.S * MPK;
+    for (int i = ctid * 4; i < p.M * kBN; i += kWarps * 32 * 4) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int ss = 0; ss < p.S; ++ss) {
+        const float4 b = __ldcg(reinterpret_cast<const float4*>(wsg + (size_t)ss * MPK + i));
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      *reinterpret_cast<float4*>(fs + i) = a;
+    }
+    if (ctid == 0) p.counters[ng] = 0;  // re-arm for the next launch / graph replay
+    named_bar_sync(1, kWarps * 32);
+  }
+
+  // ---- final: alpha, bias, activation, residual, bf16 store (coalesced along n)
+  for (int i = ctid; i < p.M * (kBN / 2); i += kWarps * 32) {
+    const int m = i / (kBN / 2), np = i - m * (kBN / 2);
+    const int n = ng * kBN + np * 2;
+    if (n >= p.N) continue;
+    float v0 = fs[m * kBN + np * 2] * p.alpha, v1 = fs[m * kBN + np * 2 + 1] * p.alpha;
+    const bool has1 = (n + 1) < p.N;
+    if (p.bias) {
+      v0 += __bfloat162float(p.bias[n]);
+      if (has1) v1 += __bfloat162float(p.bias[n + 1]);
+    }
+    v0 = apply_act_rt(v0, p.act);
+    v1 = apply_act_rt(v1, p.act);
+    __nv_bfloat16* cp = p.C + (int64_t)m * p.ldc + n;
+    if (p.residual) {
+      const __nv_bfloat16* rp = p.residual + (int64_t)m * p.ldc + n;
+      v0 += __bfloat162float(rp[0]);
+      if (has1) v1 += __bfloat162float(rp[1]);
+    }
+    if (has1 && ((reinterpret_cast<uintptr_t>(cp) & 3) == 0)) {
+      *reinterpret_cast<uint32_t*>(cp) = pack_bf16x2(v0, v1);
+    } else {
+      cp[0] = __float2bfloat16(v0);
+      if (has1) cp[1] = __float2bfloat16(v1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// init-time re-layout kernels (reference layouts -> tile image).  One thread per 32-bit word.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void frag_coord(int g, int t, int j, int r, int e, int& dn, int& dk) {
+  dn = g + 8 * (r & 1);
+  dk = 16 * t + 4 * j + 2 * (r >> 1) + e;
+}
+
+__global__ void pack_w4_kernel(uint32_t* __restrict__ dst, const uint8_t* __restrict__ q, int K, int N, int KT, int NG) {
+  const int64_t total = (int64_t)NG * KT * kWarps * 32 * 4;
+  const int npack = (N + 1) / 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = i & 3;
+    const int lane = (i >> 2) & 31;
+    const int w = (i >> 7) & 7;
+    const int64_t tile = i >> 10;
+    const int kt = tile % KT, ng = tile / KT;
+    const int g = lane >> 2, t = lane & 3;
+    uint32_t word = 0;
+    for (int r = 0; r < 4; ++r)
+      for (int e = 0; e < 2; ++e) {
+        int dn, dk;
+        frag_coord(g, t, j, r, e, dn, dk);
+        const int n = ng * kBN + w * 16 + dn, k = kt * kBK + dk;
+        uint32_t v = 0;
+        if (n < N && k < K) {
+          const uint8_t b = q[(int64_t)k * npack + (n >> 1)];
+          v = (n & 1) ? (b >> 4) : (b & 0xF);
+        }
+        word |= v << (4 * (r + 4 * e));
+      }
+    dst[i] = (word << 3) | (word >> 29);
+  }
+}
+
+__global__ void pack_w8_kernel(uint32_t* __restrict__ dst, const uint8_t* __restrict__ q, int K, int N, int KT, int NG,
+                               int is_signed) {
+  const int64_t total = (int64_t)NG * KT * kWarps * 2 * 32 * 4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = i & 3;
+    const int lane = (i >> 2) & 31;
+    const int c = (i >> 7) & 1;
+    const int w = (i >> 8) & 7;
+    const int64_t tile = i >> 11;
+    const int kt = tile % KT, ng = tile / KT;
+    const int g = lane >> 2, t = lane & 3;
+    const int j = 2 * c + (x >> 1), h = x & 1;
+    uint32_t word = 0;
+    for (int b = 0; b < 4; ++b) {
+      const int r = 2 * h + (b & 1), e = b >> 1;
+      int dn, dk;
+      frag_coord(g, t, j, r, e, dn, dk);
+      const int n = ng * kBN + w * 16 + dn, k = kt * kBK + dk;
+      uint32_t v = is_signed ? 0x80u : 0u;
+      if (n < N && k < K) v = q[(int64_t)k * N + n] ^ (is_signed ? 0x80u : 0u);
+      word |= v << (8 * b);
+    }
+    dst[i] = (word << 3) | (word >> 29);
+  }
+}
+
+__global__ void pack_w16_kernel(uint32_t* __restrict__ dst, const uint16_t* __restrict__ wsrc, int K, int N, int KT, int NG) {
+  const int64_t total = (int64_t)NG * KT * kWarps * 4 * 32 * 4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = i & 3;
+    const int lane = (i >> 2) & 31;
+    const int j = (i >> 7) & 3;
+    const int w = (i >> 9) & 7;
+    const int64_t tile = i >> 12;
+    const int kt = tile % KT, ng = tile / KT;
+    const int g = lane >> 2, t = lane & 3;
+    uint32_t word = 0;
+    for (int e = 0; e < 2; ++e) {
+      int dn, dk;
+      frag_coord(g, t, j, r, e, dn, dk);
+      const int n = ng * kBN + w * 16 + dn, k = kt * kBK + dk;
+      uint32_t v = 0;
+      if (n < N && k < K) v = wsrc[(int64_t)k * N + n];
+      word |= v << (16 * e);
+    }
+    dst[i] = word;
+  }
+}
+
+// (scale, zero) bf16 [G][N] -> float2 [G][Np] with the integer-bias constant folded into the zero
+__global__ void pack_sz_kernel(float2* __restrict__ dst, const __nv_bfloat16* __restrict__ scales,
+                               const __nv_bfloat16* __restrict__ zeros, int G, int N, int Np, float zbias) {
+  const int64_t total = (int64_t)G * Np;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = i % Np, gi = i / Np;
+    float2 v = make_float2(0.f, 0.f);
+    if (n < N) v = make_float2(__bfloat162float(scales[(int64_t)gi * N + n]), __bfloat162float(zeros[(int64_t)gi * N + n]) + zbias);
+    dst[i] = v;
+  }
+}
+
+}  // namespace b2
+
+// ================================================================================================
+// host side
+// ================================================================================================
+using namespace b2;
+
+struct Plan {
+  bool valid = false;
+  int S = 1, xt = 1, nstage = 4, smem = 0, quanta = 1;
+};
+
+struct b2_gemm_wq {
+  b2_gemm_wq_desc d;
+  int Kp = 0, Np = 0, KT = 0, NG = 0, G = 1, group_tiles = 0;
+  size_t tile_bytes = 0, packed_bytes = 0;
+  void* packed = nullptr;
+  bool own_packed = false;
+  float2* sz = nullptr;
+  bool own_sz = false;
+  unsigned* counters = nullptr;
+  Plan plans[3];  // MT = 1, 2, 4
+  int device = 0;
+};
+
+typedef void (*gemm_kernel_t)(const GemmParams);
+
+template <int WBITS, bool GROUPED>
+static gemm_kernel_t pick_mt(int mt) {
+  switch (mt) {
+    case 1: return wq_gemm_kernel<WBITS, 1, GROUPED>;
+    case 2: return wq_gemm_kernel<WBITS, 2, GROUPED>;
+    default: return wq_gemm_kernel<WBITS, 4, GROUPED>;
+  }
+}
+static gemm_kernel_t pick_kernel(int wbits, bool grouped, int mt) {
+  if (wbits == 4) return grouped ? pick_mt<4, true>(mt) : pick_mt<4, false>(mt);
+  if (wbits == 8) return grouped ? pick_mt<8, true>(mt) : pick_mt<8, false>(mt);
+  return pick_mt<16, false>(mt);
+}
+static int stage_bytes_of(int wbits) { return wbits == 16 ? WTraits<16>::STAGE_BYTES : kStageBytes; }
+static int tile_bytes_of(int wbits) { return wbits == 4 ? WTraits<4>::TILE_BYTES : (wbits == 8 ? WTraits<8>::TILE_BYTES : WTraits<16>::TILE_BYTES); }
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+static int make_plan(b2_gemm_wq* h, int mti) {
+  Plan& pl = h->plans[mti];
+  if (pl.valid) return B2_OK;
+  const int mt = 1 << mti, MP = 8 * mt;
+  const bool grouped = h->group_tiles > 0;
+  const int gt = grouped ? h->group_tiles : 1;
+  const int quanta = h->KT / gt;
+  const int sms = sm_count();
+  gemm_kernel_t kern = pick_kernel(h->d.wbits, grouped, mt);
+  const int nstage = env_int("B2_GEMM_STAGES", h->d.wbits == 16 ? 3 : 6);
+  const int x_budget = env_int("B2_GEMM_XBYTES", 20 * 1024);
+  // activation chunk: as many k-tiles as fit the budget, a multiple of the quant group
+  int xt_cap = (x_budget / MP - 16) / 128;
+  xt_cap = xt_cap / gt * gt;
+  if (xt_cap < gt) xt_cap = gt;
+  auto smem_for = [&](int xt) {
+    const int gpc = grouped ? xt / gt : 1;
+    return nstage * stage_bytes_of(h->d.wbits) + MP * (xt * 128 + 16) + MP * kBN * 4 + MP * gpc * 4 + 16 + 8 + nstage * 16 + 64;
+  };
+  // first guess occupancy with the cap, derive S, then shrink xt to what a unit really needs
+  int smem = smem_for(xt_cap);
+  B2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin()));
+  int occ = 1;
+  B2_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
+  if (occ < 1) occ = 1;
+  const int slots = occ * sms;
+  int S = slots / h->NG;
+  const int min_quanta = (2 + gt - 1) / gt;  // at least ~2 k-tiles per unit
+  if (S > quanta / (min_quanta > 0 ? min_quanta : 1)) S = quanta / (min_quanta > 0 ? min_quanta : 1);
+  const int smax = env_int("B2_GEMM_MAX_SPLIT", 32);
+  if (S > smax) S = smax;
+  if (S < 1) S = 1;
+  const int force = env_int("B2_GEMM_FORCE_SPLIT", 0);
+  if (force > 0) S = force < quanta ? force : quanta;
+  const int unit_tiles = ((quanta + S - 1) / S) * gt;
+  int xt = unit_tiles < xt_cap ? unit_tiles : xt_cap;
+  xt = (xt + gt - 1) / gt * gt;
+  pl.S = S;
+  pl.xt = xt;
+  pl.nstage = nstage;
+  pl.smem = smem_for(xt);
+  pl.quanta = quanta;
+  pl.valid = true;
+  return B2_OK;
+}
+
+extern "C" {
+
+int b2_gemm_wq_create(b2_gemm_wq_t* out, const b2_gemm_wq_desc* d) {
+  if (!out || !d) return B2_ERR_PARAM;
+  if (d->K <= 0 || d->N <= 0 || d->max_m <= 0) return B2_ERR_PARAM;
+  if (d->wbits != 4 && d->wbits != 8 && d->wbits != 16) return B2_ERR_PARAM;
+  if (d->ft != B2_DT_BF16) return B2_ERR_UNSUPPORTED;
+  if (d->wbits == 4 && d->qtype != B2_DT_U8) return B2_ERR_PARAM;  // gemm_a16w4.cpp:104-110: uint8(uint4x2) only
+  if (d->wbits == 8 && d->qtype != B2_DT_U8 && d->qtype != B2_DT_I8) return B2_ERR_PARAM;
+  if (d->K % 8 != 0) return B2_ERR_UNSUPPORTED;
+  if (d->wbits != 16 && d->group_size != -1) {
+    if (d->group_size <= 0 || d->group_size % kBK != 0) return B2_ERR_UNSUPPORTED;
+  }
+  b2_gemm_wq* h = new (std::nothrow) b2_gemm_wq();
+  if (!h) return B2_ERR_RUNTIME;
+  h->d = *d;
+  const bool grouped = d->wbits != 16 && d->group_size != -1;
+  const int kq = grouped ? d->group_size : kBK;
+  h->Kp = (d->K + kq - 1) / kq * kq;
+  h->Np = (d->N + kBN - 1) / kBN * kBN;
+  h->KT = h->Kp / kBK;
+  h->NG = h->Np / kBN;
+  h->group_tiles = grouped ? d->group_size / kBK : 0;
+  h->G = grouped ? h->Kp / d->group_size : 1;
+  h->tile_bytes = tile_bytes_of(d->wbits);
+  h->packed_bytes = (size_t)h->NG * h->KT * h->tile_bytes;
+  cudaGetDevice(&h->device);
+  cudaError_t e = cudaMalloc(&h->counters, sizeof(unsigned) * h->NG);
+  if (e == cudaSuccess) e = cudaMemset(h->counters, 0, sizeof(unsigned) * h->NG);
+  if (e != cudaSuccess) {
+    set_last_error("b2_gemm_wq_create", e);
+    delete h;
+    return B2_ERR_CUDA;
+  }
+  *out = h;
+  return B2_OK;
+}
+
+int b2_gemm_wq_destroy(b2_gemm_wq_t h) {
+  if (!h) return B2_OK;
+  if (h->own_packed && h->packed) cudaFree(h->packed);
+  if (h->own_sz && h->sz) cudaFree(h->sz);
+  if (h->counters) cudaFree(h->counters);
+  delete h;
+  return B2_OK;
+}
+
+size_t b2_gemm_wq_packed_bytes(b2_gemm_wq_t h) { return h ? h->packed_bytes : 0; }
+
+int b2_gemm_wq_prepare_weights(b2_gemm_wq_t h, const void* qdata, const void* scales, const void* zeros,
+                               void* packed_dst, void* stream_) {
+  if (!h || !qdata) return B2_ERR_PARAM;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const b2_gemm_wq_desc& d = h->d;
+  if (d.wbits != 16 && (!scales || !zeros)) return B2_ERR_PARAM;
+  if (packed_dst) {
+    if (h->own_packed && h->packed) cudaFree(h->packed);
+    h->packed = packed_dst;
+    h->own_packed = false;
+  } else if (!h->packed || !h->own_packed) {
+    B2_CUDA_TRY(cudaMalloc(&h->packed, h->packed_bytes));
+    h->own_packed = true;
+  }
+  const int threads = 256;
+  const int64_t words = (int64_t)h->packed_bytes / 4;
+  const int blocks = (int)((words + threads - 1) / threads > 65535 * 8 ? 65535 * 8 : (words + threads - 1) / threads);
+  if (d.wbits == 4)
+    pack_w4_kernel<<<blocks, threads, 0, stream>>>((uint32_t*)h->packed, (const uint8_t*)qdata, d.K, d.N, h->KT, h->NG);
+  else if (d.wbits == 8)
+    pack_w8_kernel<<<blocks, threads, 0, stream>>>((uint32_t*)h->packed, (const uint8_t*)qdata, d.K, d.N, h->KT, h->NG,
+                                                   d.qtype == B2_DT_I8);
+  else
+    pack_w16_kernel<<<blocks, threads, 0, stream>>>((uint32_t*)h->packed, (const uint16_t*)qdata, d.K, d.N, h->KT, h->NG);
+  if (int st = launch_failed("pack_weights")) return st;
+  if (d.wbits != 16) {
+    if (!h->sz || !h->own_sz) {
+      B2_CUDA_TRY(cudaMalloc(&h->sz, sizeof(float2) * (size_t)h->G * h->Np));
+      h->own_sz = true;
+    }
+    // 16+q trick: W4 raw = sum a*(16+q); W8 raw = 16*sum a*(16+hi) + sum a*(16+lo) = sum a*(272+u), u = q (+128 if int8)
+    const float zbias = d.wbits == 4 ? 16.f : (d.qtype == B2_DT_I8 ? 272.f + 128.f : 272.f);
+    // scales/zeros given for ceil(K/group) groups; groups beyond that (K padding) never occur since Kp/group == ceil
+    const int64_t tot = (int64_t)h->G * h->Np;
+    pack_sz_kernel<<<(int)((tot + 255) / 256), 256, 0, stream>>>(h->sz, (const __nv_bfloat16*)scales,
+                                                                 (const __nv_bfloat16*)zeros, h->G, d.N, h->Np, zbias);
+    if (int st = launch_failed("pack_sz")) return st;
+  }
+  return B2_OK;
+}
+
+int b2_gemm_wq_attach_packed(b2_gemm_wq_t h, const void* packed, const void* scales_f32, const void* zeros_f32) {
+  (void)zeros_f32;
+  if (!h || !packed) return B2_ERR_PARAM;
+  if (h->own_packed && h->packed) cudaFree(h->packed);
+  h->packed = const_cast<void*>(packed);
+  h->own_packed = false;
+  if (scales_f32) {
+    if (h->own_sz && h->sz) cudaFree(h->sz);
+    h->sz = (float2*)const_cast<void*>(scales_f32);
+    h->own_sz = false;
+  }
+  return B2_OK;
+}
+
+static int mt_index_for(int M) { return M <= 8 ? 0 : (M <= 16 ? 1 : 2); }
+
+size_t b2_gemm_wq_workspace_bytes(b2_gemm_wq_t h, int M) {
+  if (!h || M <= 0) return 0;
+  const int mc = M > 32 ? 32 : M;
+  const int mti = mt_index_for(mc);
+  if (make_plan(h, mti) != B2_OK) return 0;
+  const Plan& pl = h->plans[mti];
+  if (pl.S <= 1) return 16;
+  return (size_t)h->NG * pl.S * (8 << mti) * kBN * sizeof(float) + 16;
+}
+
+size_t b2_gemm_wq_algo_bytes(b2_gemm_wq_t h, int M) {
+  if (!h) return 0;
+  const b2_gemm_wq_desc& d = h->d;
+  size_t w = (size_t)d.K * d.N * d.wbits / 8;
+  size_t prm = d.wbits == 16 ? 0 : (size_t)2 * 2 * h->G * d.N;
+  return w + prm + (size_t)2 * M * ((size_t)d.K + d.N);
+}
+
+int b2_gemm_wq_run(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, int64_t ldc, int M, const void* bias,
+                   const void* residual, int activation, float alpha, void* workspace, size_t workspace_bytes,
+                   void* stream_) {
+  if (!h || !A || !C || M <= 0) return B2_ERR_PARAM;
+  if (!h->packed) return B2_ERR_RUNTIME;
+  if (M > h->d.max_m) return B2_ERR_LIMIT;
+  if (activation < 0 || activation > B2_ACT_SIGMOID) return B2_ERR_PARAM;
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (lda % 8) != 0) return B2_ERR_UNSUPPORTED;
+  if (workspace_bytes < b2_gemm_wq_workspace_bytes(h, M)) return B2_ERR_PARAM;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const bool grouped = h->group_tiles > 0;
+  for (int m0 = 0; m0 < M; m0 += 32) {
+    const int mc = (M - m0) > 32 ? 32 : (M - m0);
+    const int mti = mt_index_for(mc);
+    if (int st = make_plan(h, mti)) return st;
+    const Plan& pl = h->plans[mti];
+    if (pl.S > 1 && !workspace) return B2_ERR_PARAM;
+    GemmParams p;
+    p.packed = (const uint8_t*)h->packed;
+    p.sz = h->sz;
+    p.A = (const __nv_bfloat16*)A + (int64_t)m0 * lda;
+    p.lda = lda;
+    p.C = (__nv_bfloat16*)C + (int64_t)m0 * ldc;
+    p.ldc = ldc;
+    p.bias = (const __nv_bfloat16*)bias;
+    p.residual = residual ? (const __nv_bfloat16*)residual + (int64_t)m0 * ldc : nullptr;
+    p.ws = (float*)workspace;
+    p.counters = h->counters;
+    p.M = mc; p.N = h->d.N; p.K = h->d.K; p.Np = h->Np; p.KT = h->KT; p.NG = h->NG; p.S = pl.S;
+    p.group_tiles = h->group_tiles;
+    p.quanta = pl.quanta;
+    p.xt = pl.xt;
+    p.nstage = pl.nstage;
+    p.act = activation;
+    p.alpha = alpha;
+    gemm_kernel_t kern = pick_kernel(h->d.wbits, grouped, 1 << mti);
+    cudaError_t e = launch(kern, dim3(h->NG * pl.S), dim3(kThreads), (size_t)pl.smem, stream, true, p);
+    if (e != cudaSuccess) {
+      set_last_error("wq_gemm launch", e);
+      return B2_ERR_CUDA;
+    }
+  }
+  return B2_OK;
+}
+
+}  // extern "C"

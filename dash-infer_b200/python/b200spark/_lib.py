@@ -1,0 +1,92 @@
+"""ctypes binding of include/b200spark.h.  There is NO fallback: if the native library is missing the
+import fails loudly (build it with `python dash-infer_b200/build.py`)."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_DIR = os.path.normpath(os.path.join(_HERE, "..", "..", "lib"))
+LIB_PATH = os.path.join(LIB_DIR, "libb200spark.so")
+
+# every symbol include/b200spark.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "b2_status_string", "b2_last_error", "b2_version", "b2_set_pdl",
+    "b2_gemm_wq_create", "b2_gemm_wq_destroy", "b2_gemm_wq_packed_bytes", "b2_gemm_wq_prepare_weights",
+    "b2_gemm_wq_attach_packed", "b2_gemm_wq_workspace_bytes", "b2_gemm_wq_run", "b2_gemm_wq_algo_bytes",
+    "b2_span_bytes", "b2_span_cache_append", "b2_span_attn_create", "b2_span_attn_destroy",
+    "b2_span_attn_workspace_bytes", "b2_span_attn_run", "b2_span_attn_algo_bytes",
+    "b2_rmsnorm", "b2_rotary", "b2_binary", "b2_embedding", "b2_argmax", "b2_lens_add",
+]
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [("K", C.c_int32), ("N", C.c_int32), ("wbits", C.c_int32), ("group_size", C.c_int32),
+                ("ft", C.c_int32), ("qtype", C.c_int32), ("max_m", C.c_int32), ("reserved", C.c_int32)]
+
+
+class SpanCfg(C.Structure):
+    _fields_ = [("ft", C.c_int32), ("quant_mode", C.c_int32), ("n_heads", C.c_int32), ("n_groups", C.c_int32),
+                ("head_size", C.c_int32), ("span_len", C.c_int32), ("max_spans_per_seq", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class RopeCfg(C.Structure):
+    _fields_ = [("base", C.c_float), ("rotary_dim", C.c_int32), ("reserved", C.c_int32)]
+
+
+DT_F32, DT_F16, DT_I8, DT_BF16, DT_U8 = 1, 2, 3, 9, 10
+ACT_NONE, ACT_TANH, ACT_GELU_ERF, ACT_GELU_TANH, ACT_RELU, ACT_SILU, ACT_SIGMOID = range(7)
+BIN_ADD, BIN_MUL = 1, 2
+KV_NONE, KV_I8, KV_U4 = 0, 1, 2
+
+
+class B2Error(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"b200spark native library not found at {LIB_PATH}; build it first: python dash-infer_b200/build.py "
+            "(there is no CPU/PyTorch fallback for the hot path)")
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, i32, i64, sz, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float
+    sig = {
+        "b2_status_string": (C.c_char_p, [i32]),
+        "b2_last_error": (C.c_char_p, []),
+        "b2_version": (C.c_char_p, []),
+        "b2_set_pdl": (None, [i32]),
+        "b2_gemm_wq_create": (i32, [C.POINTER(vp), C.POINTER(GemmDesc)]),
+        "b2_gemm_wq_destroy": (i32, [vp]),
+        "b2_gemm_wq_packed_bytes": (sz, [vp]),
+        "b2_gemm_wq_prepare_weights": (i32, [vp, vp, vp, vp, vp, vp]),
+        "b2_gemm_wq_attach_packed": (i32, [vp, vp, vp, vp]),
+        "b2_gemm_wq_workspace_bytes": (sz, [vp, i32]),
+        "b2_gemm_wq_run": (i32, [vp, vp, i64, vp, i64, i32, vp, vp, i32, f32, vp, sz, vp]),
+        "b2_gemm_wq_algo_bytes": (sz, [vp, i32]),
+        "b2_span_bytes": (sz, [C.POINTER(SpanCfg)]),
+        "b2_span_cache_append": (i32, [C.POINTER(SpanCfg), vp, vp, vp, vp, vp, i32, C.POINTER(RopeCfg), vp]),
+        "b2_span_attn_create": (i32, [C.POINTER(vp), C.POINTER(SpanCfg), i32]),
+        "b2_span_attn_destroy": (i32, [vp]),
+        "b2_span_attn_workspace_bytes": (sz, [vp, i32, i32]),
+        "b2_span_attn_run": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, vp, sz, f32, vp]),
+        "b2_span_attn_algo_bytes": (sz, [C.POINTER(SpanCfg), i64]),
+        "b2_rmsnorm": (i32, [vp, vp, vp, i32, i32, f32, vp]),
+        "b2_rotary": (i32, [vp, vp, i32, i32, i32, i32, C.POINTER(RopeCfg), vp]),
+        "b2_binary": (i32, [vp, vp, vp, i64, i32, vp]),
+        "b2_embedding": (i32, [vp, vp, vp, i32, i32, vp]),
+        "b2_argmax": (i32, [vp, vp, i32, i32, i64, vp]),
+        "b2_lens_add": (i32, [vp, i32, i32, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError here == ABI drift: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(status, what=""):
+    if status != 0:
+        raise B2Error(f"{what}: {lib.b2_status_string(status).decode()} ({lib.b2_last_error().decode()})")

@@ -1,0 +1,196 @@
+"""Torch-tensor front end over the C ABI (device memory + streams come from torch; compute does not).
+
+Every call goes through include/b200spark.h on torch's current CUDA stream.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_NONE, BIN_ADD, BIN_MUL, DT_BF16, DT_I8, DT_U8, KV_I8, KV_NONE, KV_U4, GemmDesc, RopeCfg,
+                   SpanCfg, check, lib)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class Workspace:
+    """The shared 'workspace' tensor of the reference's TensorMap: one buffer reused by every op, grown on demand
+    (AsTensor::SetShape semantics, csrc/core/tensor/tensor.cpp:721-746)."""
+
+    def __init__(self, device="cuda"):
+        self.device = device
+        self.buf = torch.empty(256, dtype=torch.uint8, device=device)
+
+    def reserve(self, nbytes):
+        if self.buf.numel() < nbytes:
+            self.buf = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
+        return self.buf
+
+
+class GemmWQ:
+    """GemmA16W4 / GemmA16W8 / dense Gemm (wbits 16) handle."""
+
+    def __init__(self, K, N, wbits, group_size=-1, max_m=64, signed=True):
+        self.K, self.N, self.wbits, self.group_size, self.max_m = K, N, wbits, group_size, max_m
+        self.h = C.c_void_p()
+        qtype = DT_U8 if wbits == 4 or not signed else DT_I8
+        d = GemmDesc(K, N, wbits, group_size if wbits != 16 else -1, DT_BF16, qtype, max_m, 0)
+        check(lib.b2_gemm_wq_create(C.byref(self.h), C.byref(d)), "b2_gemm_wq_create")
+        self.bias = None
+
+    def prepare(self, qdata, scales=None, zeros=None, bias=None):
+        assert qdata.is_cuda and qdata.is_contiguous()
+        if self.wbits != 16:
+            assert scales.dtype == torch.bfloat16 and zeros.dtype == torch.bfloat16
+            scales, zeros = scales.contiguous(), zeros.contiguous()
+        check(lib.b2_gemm_wq_prepare_weights(self.h, _ptr(qdata), _ptr(scales), _ptr(zeros), None, _stream()),
+              "b2_gemm_wq_prepare_weights")
+        self.bias = bias.contiguous() if bias is not None else None
+        torch.cuda.current_stream().synchronize()  # the caller may free qdata right after
+        return self
+
+    def workspace_bytes(self, M):
+        return lib.b2_gemm_wq_workspace_bytes(self.h, M)
+
+    def algo_bytes(self, M):
+        return lib.b2_gemm_wq_algo_bytes(self.h, M)
+
+    def packed_bytes(self):
+        return lib.b2_gemm_wq_packed_bytes(self.h)
+
+    def __call__(self, a, ws, out=None, act=ACT_NONE, alpha=1.0, residual=None):
+        M = a.numel() // a.shape[-1]
+        assert a.dtype == torch.bfloat16 and a.shape[-1] == self.K and a.stride(-1) == 1
+        if out is None:
+            out = torch.empty(*a.shape[:-1], self.N, dtype=torch.bfloat16, device=a.device)
+        wsb = ws.reserve(self.workspace_bytes(M))
+        lda = a.stride(-2) if a.dim() > 1 else self.K
+        ldc = out.stride(-2) if out.dim() > 1 else self.N
+        check(lib.b2_gemm_wq_run(self.h, _ptr(a), lda, _ptr(out), ldc, M, _ptr(self.bias), _ptr(residual), act,
+                                 float(alpha), _ptr(wsb), wsb.numel(), _stream()), "b2_gemm_wq_run")
+        return out
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib.b2_gemm_wq_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class SpanCache:
+    """Test/bench stand-in for the reference's CacheSpanManager + SpannedVirtualCache: owns span pages for one
+    layer's K and V of a batch and the device pointer tables [batch, max_spans] the kernels walk."""
+
+    def __init__(self, batch, max_len, n_heads, n_groups, span_len=128, quant_mode=KV_NONE, device="cuda", pool=None):
+        self.batch, self.max_len = batch, max_len
+        self.max_spans = (max_len + span_len - 1) // span_len
+        self.cfg = SpanCfg(DT_BF16, quant_mode, n_heads, n_groups, 128, span_len, self.max_spans, 0)
+        self.span_bytes = lib.b2_span_bytes(C.byref(self.cfg))
+        assert self.span_bytes > 0, "bad span config"
+        n = batch * self.max_spans
+        stride = (self.span_bytes + 255) // 256 * 256
+        self.stride = stride
+        # pages deliberately handed out in a scrambled order: the kernels must not assume contiguity
+        self.k_pool = torch.zeros(n * stride, dtype=torch.uint8, device=device)
+        self.v_pool = torch.zeros(n * stride, dtype=torch.uint8, device=device)
+        g = torch.Generator().manual_seed(99)
+        perm_k = torch.randperm(n, generator=g)
+        perm_v = torch.randperm(n, generator=g)
+        self.k_tab = (self.k_pool.data_ptr() + perm_k * stride).to(torch.int64).reshape(batch, self.max_spans).to(device)
+        self.v_tab = (self.v_pool.data_ptr() + perm_v * stride).to(torch.int64).reshape(batch, self.max_spans).to(device)
+        self.perm_k, self.perm_v = perm_k.reshape(batch, -1), perm_v.reshape(batch, -1)
+
+    def span_view(self, which, b, si):
+        pool, perm = (self.k_pool, self.perm_k) if which == "k" else (self.v_pool, self.perm_v)
+        off = int(perm[b, si]) * self.stride
+        return pool[off: off + self.span_bytes]
+
+
+def cache_append(cache, qkv, old_lens, q_out=None, rope=None):
+    cfg = cache.cfg
+    B = qkv.shape[0]
+    if q_out is None:
+        q_out = torch.empty(B, cfg.n_heads * 128, dtype=torch.bfloat16, device=qkv.device)
+    r = RopeCfg(float(rope[0]), int(rope[1]), 0) if rope is not None else None
+    check(lib.b2_span_cache_append(C.byref(cfg), _ptr(cache.k_tab), _ptr(cache.v_tab), _ptr(q_out), _ptr(qkv),
+                                   _ptr(old_lens), B, C.byref(r) if r is not None else None, _stream()),
+          "b2_span_cache_append")
+    return q_out
+
+
+class SpanAttn:
+    def __init__(self, cfg, max_batch):
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        check(lib.b2_span_attn_create(C.byref(self.h), C.byref(cfg), max_batch), "b2_span_attn_create")
+
+    def workspace_bytes(self, batch, max_len):
+        return lib.b2_span_attn_workspace_bytes(self.h, batch, max_len)
+
+    def __call__(self, q, cache, new_lens, max_len, ws, out=None, scale=None):
+        B = q.shape[0]
+        if out is None:
+            out = torch.empty_like(q)
+        if scale is None:
+            scale = 1.0 / (128 ** 0.5)
+        wsb = ws.reserve(self.workspace_bytes(B, max_len))
+        check(lib.b2_span_attn_run(self.h, _ptr(out), _ptr(q), _ptr(cache.k_tab), _ptr(cache.v_tab), _ptr(new_lens), B,
+                                   int(max_len), _ptr(wsb), wsb.numel(), float(scale), _stream()), "b2_span_attn_run")
+        return out
+
+    def algo_bytes(self, total_tokens):
+        return lib.b2_span_attn_algo_bytes(C.byref(self.cfg), int(total_tokens))
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib.b2_span_attn_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def rmsnorm(x, gamma, eps=1e-6, out=None):
+    out = torch.empty_like(x) if out is None else out
+    cols = x.shape[-1]
+    check(lib.b2_rmsnorm(_ptr(out), _ptr(x), _ptr(gamma), x.numel() // cols, cols, float(eps), _stream()), "b2_rmsnorm")
+    return out
+
+
+def rotary(qkv, pos, n_heads, n_groups, base=1e6, rotary_dim=128):
+    r = RopeCfg(float(base), int(rotary_dim), 0)
+    check(lib.b2_rotary(_ptr(qkv), _ptr(pos), qkv.shape[0], n_heads, n_groups, 128, C.byref(r), _stream()), "b2_rotary")
+    return qkv
+
+
+def binary(a, b, op, out=None):
+    out = torch.empty_like(a) if out is None else out
+    check(lib.b2_binary(_ptr(out), _ptr(a), _ptr(b), a.numel(), op, _stream()), "b2_binary")
+    return out
+
+
+def embedding(table, ids, out=None):
+    B, H = ids.numel(), table.shape[1]
+    out = torch.empty(B, H, dtype=table.dtype, device=table.device) if out is None else out
+    check(lib.b2_embedding(_ptr(out), _ptr(table), _ptr(ids), B, H, _stream()), "b2_embedding")
+    return out
+
+
+def argmax(logits, out=None):
+    B, n = logits.shape
+    out = torch.empty(B, dtype=torch.int64, device=logits.device) if out is None else out
+    check(lib.b2_argmax(_ptr(out), _ptr(logits), B, n, logits.stride(0), _stream()), "b2_argmax")
+    return out
+
+
+def lens_add(lens, delta):
+    check(lib.b2_lens_add(_ptr(lens), lens.numel(), int(delta), _stream()), "b2_lens_add")
+    return lens

@@ -1,0 +1,184 @@
+/*
+ * b200spark C ABI — the drop-in boundary for DashInfer's quantized decode hot path on B200 (sm_100a).
+ *
+ * Everything here is `extern "C"`, takes plain pointers / sizes / POD structs and returns an `int`
+ * status (b2_status); nothing throws, nothing synchronises the device, every call is ordered on the
+ * `stream` it is given (a `cudaStream_t` passed as `void*`).  Enum values on the wire are the
+ * reference's own (allspark.proto DataType / UnaryType, span::QuantMode), so the C++ operator shims
+ * (dash-infer_b200/host/) forward attributes unchanged.
+ *
+ * Reference interfaces replaced (paths relative to modelscope/dash-infer @ f3cca8e):
+ *   b2_gemm_wq_*          cuda::GemmA16W4Launcher::Run / GetWorkSpaceSize
+ *                           csrc/core/kernel/cuda/gemm_lowp/gemm_a16w4_kernel.h:133-273
+ *                         cuda::GemmA16W8Launcher::Run
+ *                           csrc/core/kernel/cuda/gemm_lowp/gemm_a16w8_kernel.h:229-330
+ *                         weight re-layout at op init (GemmA16W8GPU::B_I8_Reorder...)
+ *                           csrc/core/operator/general/gemm_lowp/gemm_a16w8_gpu.cpp:422-473
+ *                         dense Gemm (lm_head): cuda::GemmWraper  csrc/core/kernel/cuda/gemm.cu:596-615
+ *   b2_span_bytes         CacheUtils::GetSpanSizeInBytes  csrc/runtime/cache/virtual_cache.cpp:202-232
+ *   b2_span_cache_append  cuda::DecoderCacheAppendLauncher
+ *                           csrc/core/kernel/cuda/cache/decoder_cache_append.cuh:102-185
+ *   b2_span_attn_*        span::CreateHandle/GetDeviceWorkspaceSize/Run/DestroyHandle
+ *                           span-attention/include/spanattn/span_attn.h:108-175
+ *   b2_rmsnorm, b2_rotary, b2_binary, b2_embedding, b2_argmax ("next" rows)
+ *                         LayerNormNoBeta / Rotary / Binary / EmbeddingT5 / GenerateOp(top_k=1)
+ *                           csrc/core/kernel/cuda/layernorm.cu:86, rotary.cu:23, binary.cu
+ */
+#ifndef B200SPARK_H_
+#define B200SPARK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes (map 1:1 onto span::SaStatus, span_attn.h:53-70; AsStatus in the shims) ---- */
+typedef enum {
+  B2_OK = 0,
+  B2_ERR_CUDA = 1,
+  B2_ERR_RUNTIME = 2,
+  B2_ERR_PARAM = 3,
+  B2_ERR_LIMIT = 4,
+  B2_ERR_INTERNAL = 5,
+  B2_ERR_UNSUPPORTED = 6
+} b2_status;
+
+const char* b2_status_string(int status);
+/* Last CUDA error text recorded by a failing call on this thread (empty string if none). */
+const char* b2_last_error(void);
+/* "b200spark <ver> sm_100a" */
+const char* b2_version(void);
+
+/* ---- allspark.proto wire enums (csrc/proto/allspark.proto:35-76) ---- */
+enum { B2_DT_F32 = 1, B2_DT_F16 = 2, B2_DT_I8 = 3, B2_DT_BF16 = 9, B2_DT_U8 = 10 };
+enum { B2_ACT_NONE = 0, B2_ACT_TANH = 1, B2_ACT_GELU_ERF = 2, B2_ACT_GELU_TANH = 3, B2_ACT_RELU = 4,
+       B2_ACT_SILU = 5, B2_ACT_SIGMOID = 6 };
+enum { B2_BIN_ADD = 1, B2_BIN_MUL = 2 };
+/* span::QuantMode (span_attn.h:41-48) */
+enum { B2_KV_NONE = 0, B2_KV_I8 = 1, B2_KV_U4 = 2 };
+
+/* =====================================================================================
+ * Weight-only quantized GEMV/GEMM:  C[M,N] = act(alpha * A[M,K] x dequant(W)[K,N] + bias) (+ residual)
+ *   wbits 4 : qdata uint8 [K, ceil(N/2)], lo nibble = even column   (GemmA16W4, gemm_a16w4.h:14-33)
+ *   wbits 8 : qdata int8/uint8 [K, N]                               (GemmA16W8)
+ *   wbits 16: unquantized FT weights [K, N] (dense Gemm / lm_head), scales/zeros ignored
+ *   dequant(W)[k,n] = (q[k,n] - zero[k/group, n]) * scale[k/group, n];  group_size -1 = per channel.
+ * The handle owns an init-time re-laid-out copy of the weights (the reference re-lays out at op init
+ * too); the caller's [K,N] buffers are only read during prepare and may be freed afterwards.
+ * ===================================================================================== */
+typedef struct b2_gemm_wq* b2_gemm_wq_t;
+
+typedef struct {
+  int32_t K;
+  int32_t N;
+  int32_t wbits;      /* 4, 8 or 16 */
+  int32_t group_size; /* -1 per-channel; otherwise a multiple of 64 */
+  int32_t ft;         /* B2_DT_BF16 (activations, scales, zeros, bias, output) */
+  int32_t qtype;      /* B2_DT_U8 (uint4x2 or uint8) or B2_DT_I8 (wbits 8) */
+  int32_t max_m;      /* largest M this handle will be run with (sizes persistent buffers) */
+  int32_t reserved;
+} b2_gemm_wq_desc;
+
+int b2_gemm_wq_create(b2_gemm_wq_t* handle, const b2_gemm_wq_desc* desc);
+int b2_gemm_wq_destroy(b2_gemm_wq_t handle);
+/* Bytes of the re-laid-out weight image. */
+size_t b2_gemm_wq_packed_bytes(b2_gemm_wq_t handle);
+/* Re-layout device tensors qdata/scales/zeros (reference layouts above) into the handle's image.
+ * If packed_dst != NULL the image is written there (caller-owned, >= packed_bytes, 128B aligned)
+ * instead of handle-owned memory — this is how two op instances share one image. */
+int b2_gemm_wq_prepare_weights(b2_gemm_wq_t handle, const void* qdata, const void* scales,
+                               const void* zeros, void* packed_dst, void* stream);
+/* Use an image prepared by another handle with an identical desc (prefill/decode sharing). */
+int b2_gemm_wq_attach_packed(b2_gemm_wq_t handle, const void* packed, const void* scales_f32,
+                             const void* zeros_f32);
+/* Scratch the caller must provide to _run for this M (split-K partials); may be 0. */
+size_t b2_gemm_wq_workspace_bytes(b2_gemm_wq_t handle, int M);
+/* A: [M, lda] FT, C: [M, ldc] FT, bias: [N] FT or NULL, residual: [M, ldc] FT or NULL (added after
+ * the activation).  workspace: >= workspace_bytes(M), 16B aligned, contents undefined on entry/exit. */
+int b2_gemm_wq_run(b2_gemm_wq_t handle, const void* A, int64_t lda, void* C, int64_t ldc, int M,
+                   const void* bias, const void* residual, int activation, float alpha,
+                   void* workspace, size_t workspace_bytes, void* stream);
+/* Algorithmic bytes one run at this M must read from HBM (weights + params + A + C). */
+size_t b2_gemm_wq_algo_bytes(b2_gemm_wq_t handle, int M);
+
+/* =====================================================================================
+ * SpanAttention: paged KV cache (spans) append + single-query attention, GQA, KV in FT / int8 / uint4.
+ * Span wire format (decoder_cache_append.cuh:33-92): [n_groups, span_len, head_size] of QT followed,
+ * for I8/U4, by [n_groups, span_len] of {float zero, float scale}.
+ * Span tables: device arrays [batch, max_spans_per_seq] of device pointers.
+ * ===================================================================================== */
+typedef struct {
+  int32_t ft;                /* B2_DT_BF16 */
+  int32_t quant_mode;        /* B2_KV_NONE / B2_KV_I8 / B2_KV_U4 */
+  int32_t n_heads;           /* query heads on this rank */
+  int32_t n_groups;          /* kv heads on this rank; n_heads % n_groups == 0, n_heads/n_groups <= 16 */
+  int32_t head_size;         /* 128 */
+  int32_t span_len;          /* 16, 32, 64 or 128 */
+  int32_t max_spans_per_seq; /* row stride of the span pointer tables */
+  int32_t reserved;
+} b2_span_cfg;
+
+size_t b2_span_bytes(const b2_span_cfg* cfg);
+
+/* Gather Q and append this step's K,V rows (one new token per sequence).
+ *   qkv      [batch, (n_heads + 2*n_groups) * head_size] FT (post-RoPE unless rope != NULL)
+ *   q_out    [batch, n_heads * head_size] FT
+ *   old_lens [batch] int32 device: tokens already cached (= write position)
+ * rope: optional fused rotary (NeoX rotate-half over rotary_dim, position = old_lens[b]); pass NULL
+ * when the graph has a separate Rotary op.  Quantised modes follow QuantParam<I8/U4>::Builder
+ * (span-attention/src/cache_quant/impl_i8.cuh:106-140, impl_u4.cuh:146-182) with IEEE division. */
+typedef struct {
+  float base;          /* e.g. 1e6 for Qwen2 */
+  int32_t rotary_dim;  /* <= head_size, even */
+  int32_t reserved;
+} b2_rope_cfg;
+int b2_span_cache_append(const b2_span_cfg* cfg, void* const* k_spans, void* const* v_spans,
+                         void* q_out, const void* qkv, const int32_t* old_lens, int batch,
+                         const b2_rope_cfg* rope, void* stream);
+
+/* Attention handle (replaces span::CreateHandle/DestroyHandle, span_attn.h:108-133).  Unlike the
+ * reference it is created ONCE per op (not per layer per step): tile scheduling happens on the
+ * device from new_lens, so nothing is rebuilt or copied host->device per step.  Owns only a small
+ * self-resetting counter array. */
+typedef struct b2_span_attn* b2_span_attn_t;
+int b2_span_attn_create(b2_span_attn_t* handle, const b2_span_cfg* cfg, int max_batch);
+int b2_span_attn_destroy(b2_span_attn_t handle);
+size_t b2_span_attn_workspace_bytes(b2_span_attn_t handle, int batch, int max_len);
+
+/* out [batch, n_heads*head_size] FT = softmax(qk_scale * q K^T) V over the first new_lens[b] tokens.
+ * new_lens: device int32 [batch] (including the token appended this step).  max_len bounds every
+ * new_lens[b] (only sizes the workspace check; a loose bound is fine).
+ * workspace >= workspace_bytes(batch,max_len), 16B aligned, contents undefined on entry/exit. */
+int b2_span_attn_run(b2_span_attn_t handle, void* out, const void* q, const void* const* k_spans,
+                     const void* const* v_spans, const int32_t* new_lens, int batch, int max_len,
+                     void* workspace, size_t workspace_bytes, float qk_scale, void* stream);
+/* Algorithmic KV bytes for a given total token count (sum of lens): 2 * n_groups * (row + param). */
+size_t b2_span_attn_algo_bytes(const b2_span_cfg* cfg, int64_t total_tokens);
+
+/* =====================================================================================
+ * Glue ops of the decode graph ("next" rows): element-wise / norm / lookup, FT = bf16.
+ * ===================================================================================== */
+/* y[r,:] = x[r,:] * rsqrt(mean(x^2) + eps) * gamma   (LayerNormNoBeta, layernorm.cu:86) */
+int b2_rmsnorm(void* y, const void* x, const void* gamma, int rows, int cols, float eps, void* stream);
+/* in-place NeoX rotary on the q and k heads of qkv [batch, (nH+2nG)*head]; position = pos[b] */
+int b2_rotary(void* qkv, const int32_t* pos, int batch, int n_heads, int n_groups, int head_size,
+              const b2_rope_cfg* rope, void* stream);
+/* out = a (op) b, n elements; op = B2_BIN_ADD / B2_BIN_MUL */
+int b2_binary(void* out, const void* a, const void* b, int64_t n, int op, void* stream);
+/* out[b,:] = table[ids[b],:] */
+int b2_embedding(void* out, const void* table, const int64_t* ids, int batch, int hidden, void* stream);
+/* ids_out[b] = argmax_n logits[b,n] (lowest index on ties); logits FT [batch, ld] */
+int b2_argmax(int64_t* ids_out, const void* logits, int batch, int n, int64_t ld, void* stream);
+/* lens[b] += delta for b < batch (keeps sequence lengths device-resident under CUDA graphs) */
+int b2_lens_add(int32_t* lens, int batch, int delta, void* stream);
+
+/* Programmatic dependent launch (PDL) for every kernel launched by this library on this thread:
+ * 1 = on (default), 0 = off. */
+void b2_set_pdl(int enabled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SPARK_H_ */

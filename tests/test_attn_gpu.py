@@ -1,0 +1,102 @@
+"""GPU parity: span cache append (bit-exact vs the oracle's span bytes) and paged attention through the C ABI.
+
+Attention tolerance: <= 2e-3 abs against fp32/fp64 attention on the SAME (dequantized) cache contents
+(BASELINE.md §3), inputs N(0,1) like the reference's span-attention tests (test_quant_none.cpp)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import kvcache_ref as KV
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf16(x):
+    return torch.from_numpy(x).to(torch.bfloat16)
+
+
+def _build(mode, B, lens, nH, nG, span, seed, max_len=None):
+    """Fill a device SpanCache token by token with the product append kernel and mirror it in the oracle."""
+    from b200spark import ops
+    rng = np.random.default_rng(seed)
+    max_len = max_len or (max(lens) + 1)
+    cache = ops.SpanCache(B, max_len, nH, nG, span, mode)
+    kref, vref = KV.SpanCacheRef(mode, span, nG), KV.SpanCacheRef(mode, span, nG)
+    for _ in range(B):
+        kref.add_sequence(); vref.add_sequence()
+    T = max(lens)
+    width = (nH + 2 * nG) * 128
+    q_last = np.zeros((B, nH, 128), np.float32)
+    cur = torch.zeros(B, dtype=torch.int32, device="cuda")
+    for t in range(T):
+        qkv = _bf16(rng.standard_normal((B, width)).astype(np.float32))
+        # sequences already at their final length keep re-writing a scratch position beyond their length
+        pos = torch.tensor([min(t, lens[b]) for b in range(B)], dtype=torch.int32, device="cuda")
+        q = ops.cache_append(cache, qkv.cuda(), pos)
+        x = qkv.float().numpy().reshape(B, nH + 2 * nG, 128)
+        for b in range(B):
+            if t < lens[b]:
+                kref.append(b, t, x[b, nH:nH + nG]); vref.append(b, t, x[b, nH + nG:])
+                q_last[b] = x[b, :nH]
+        if t == T - 1:
+            assert torch.equal(q.cpu().float().reshape(B, nH, 128), qkv.float().reshape(B, -1, 128)[:, :nH])
+    torch.cuda.synchronize()
+    return cache, kref, vref, q_last
+
+
+@pytest.mark.parametrize("mode", [KV.QUANT_NONE, KV.QUANT_I8, KV.QUANT_U4])
+@pytest.mark.parametrize("span", [16, 128])
+def test_append_bit_exact(mode, span):
+    B, nH, nG = 3, 8, 2
+    lens = [37, 5, 130]
+    cache, kref, vref, _ = _build(mode, B, lens, nH, nG, span, seed=span + mode, max_len=140)
+    for b in range(B):
+        for si in range((lens[b] + span - 1) // span):
+            n = min(span, lens[b] - si * span)
+            for which, ref in (("k", kref), ("v", vref)):
+                got = cache.span_view(which, b, si).cpu().numpy()
+                exp = ref.spans[b][si]
+                row = {KV.QUANT_NONE: 256, KV.QUANT_I8: 128, KV.QUANT_U4: 64}[mode]
+                for g in range(nG):  # compare only the rows/params that were written
+                    a0 = (g * span) * row
+                    assert np.array_equal(got[a0:a0 + n * row], exp[a0:a0 + n * row]), (mode, span, b, si, which, g)
+                    if mode != KV.QUANT_NONE:
+                        p0 = nG * span * row + g * span * 8
+                        assert np.array_equal(got[p0:p0 + n * 8], exp[p0:p0 + n * 8]), ("param", mode, b, si, which, g)
+
+
+@pytest.mark.parametrize("span", [16, 32, 64, 128])
+@pytest.mark.parametrize("nH,nG", [(8, 2), (7, 1), (28, 4), (16, 1)])
+def test_attention_none_small(span, nH, nG):
+    from b200spark import ops
+    lens = [1, 63, 64, 65, 200]
+    B = len(lens)
+    cache, kref, vref, q = _build(KV.QUANT_NONE, B, lens, nH, nG, span, seed=span * 31 + nH, max_len=256)
+    attn = ops.SpanAttn(cache.cfg, B)
+    ws = ops.Workspace()
+    new_lens = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    out = attn(_bf16(q.reshape(B, -1)).cuda(), cache, new_lens, 256, ws)
+    torch.cuda.synchronize()
+    ref = KV.attention_ref(q, kref, vref, lens, nH, 1.0 / np.sqrt(128))
+    err = np.abs(out.float().cpu().numpy().reshape(B, nH, 128) - ref).max()
+    assert err <= 2e-3 + 4e-3, err  # + bf16 output rounding of values up to ~1 (2^-9)
+
+
+def test_attention_none_long_and_ragged():
+    """ctx 2048 / 4100 with split-KV partials + last-CTA combine, Qwen2-7B head geometry."""
+    from b200spark import ops
+    nH, nG, span = 28, 4, 128
+    lens = [2048, 4100, 777, 2049]
+    B = len(lens)
+    cache, kref, vref, q = _build(KV.QUANT_NONE, B, lens, nH, nG, span, seed=5, max_len=4224)
+    attn = ops.SpanAttn(cache.cfg, B)
+    ws = ops.Workspace()
+    new_lens = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    qd = _bf16(q.reshape(B, -1)).cuda()
+    out = attn(qd, cache, new_lens, 4224, ws)
+    out2 = attn(qd, cache, new_lens, 4224, ws)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)  # deterministic, counters re-armed
+    ref = KV.attention_ref(q, kref, vref, lens, nH, 1.0 / np.sqrt(128))
+    err = np.abs(out.float().cpu().numpy().reshape(B, nH, 128) - ref).max()
+    assert err <= 6e-3, err

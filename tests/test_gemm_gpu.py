@@ -1,0 +1,136 @@
+"""GPU parity: weight-only GEMV/GEMM through the C ABI vs the fp32 math oracle.
+
+Tolerance: max_i min(abs, rel) <= 2e-2 (bf16) — the reference's own metric (tests/cpp/test_common.h.in:82-110) at a
+tighter bound than its 5e-1 (operator_gemm_lowp_test.cpp:650-651).  Shapes follow the reference sweep
+(M in {1,3,17,31,...}, odd N) plus the Qwen2-7B projections."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import quant_ref as Q
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2
+
+
+def _mk(K, N, M, seed, ft="bf16"):
+    g = torch.Generator().manual_seed(seed)
+    w = (torch.randn(K, N, generator=g) * 0.02).to(torch.bfloat16)
+    a = (torch.rand(M, K, generator=g) * 2 - 1).to(torch.bfloat16)
+    return w, a
+
+
+def _run(wbits, K, N, M, group, act=0, use_bias=False, use_res=False, alpha=1.0, seed=0, signed=True):
+    from b200spark import ops, quantize as PQ
+    w, a = _mk(K, N, M, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    bias = (torch.randn(N, generator=g) * 0.02).to(torch.bfloat16) if use_bias else None
+    res = (torch.randn(M, N, generator=g) * 0.1).to(torch.bfloat16) if use_res else None
+    dev = "cuda"
+    if wbits == 4:
+        qd, s, z = PQ.quantize_a16w4(w, group)
+        qu = Q.unpack_u4x2(qd.numpy(), N)
+    elif wbits == 8:
+        qd, s, z = PQ.quantize_a16w8(w, group, signed=signed)
+        qu = qd.numpy()
+    else:
+        qd, s, z = w, None, None
+    op = ops.GemmWQ(K, N, wbits, group, max_m=max(M, 1), signed=signed)
+    op.prepare(qd.to(dev), s.to(dev) if s is not None else None, z.to(dev) if z is not None else None,
+               bias.to(dev) if bias is not None else None)
+    ws = ops.Workspace()
+    out = op(a.to(dev), ws, act=act, alpha=alpha, residual=res.to(dev) if res is not None else None)
+    torch.cuda.synchronize()
+    out2 = op(a.to(dev), ws, act=act, alpha=alpha, residual=res.to(dev) if res is not None else None)  # re-armed counters
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2), "not deterministic / split-K counters not re-armed"
+    a32 = a.float().numpy()
+    if wbits == 16:
+        ref = alpha * (a32.astype(np.float64) @ w.float().numpy().astype(np.float64))
+        if bias is not None:
+            ref = ref + bias.float().numpy()[None, :]
+        ref = Q.activation(ref.astype(np.float32), act)
+    else:
+        ref = Q.gemm_wq_math(a32, qu, s.float().numpy(), z.float().numpy(), group,
+                             bias.float().numpy() if bias is not None else None, act, alpha)
+    if res is not None:
+        ref = ref + res.float().numpy()
+    got = out.float().cpu().numpy()
+    err = Q.err_min_abs_rel(ref, got)
+    assert err <= TOL, f"err {err}"
+    return err
+
+
+@pytest.mark.parametrize("M", [1, 2, 3, 8, 9, 16, 17, 31, 32, 33, 64])
+@pytest.mark.parametrize("wbits", [4, 8, 16])
+def test_small_shapes_all_m(wbits, M):
+    _run(wbits, 512, 256, M, -1, seed=M)
+
+
+@pytest.mark.parametrize("wbits,group", [(4, 128), (4, 64), (8, 128), (8, 256)])
+@pytest.mark.parametrize("M", [1, 5, 16, 32])
+def test_subchannel(wbits, group, M):
+    _run(wbits, 1024, 384, M, group, seed=7)
+
+
+@pytest.mark.parametrize("wbits", [4, 8])
+def test_odd_shapes(wbits):
+    # N not a multiple of 128 / odd N (packed nibble tail), K not a multiple of 64 (K % 8 == 0 required)
+    _run(wbits, 520, 130, 3, -1, seed=3)
+    _run(wbits, 328, 77, 1, -1, seed=4)
+    _run(wbits, 200, 48, 4, 64, seed=5)  # K padded to the group: tail group sees zero activations
+
+
+def test_uint8_weights():
+    _run(8, 512, 256, 4, -1, signed=False, seed=11)
+
+
+@pytest.mark.parametrize("act", [0, 2, 3, 4, 5])  # the lowp launchers implement none/gelu_erf/gelu_tanh/relu/silu
+def test_bias_activation(act):
+    _run(4, 512, 256, 3, -1, act=act, use_bias=True, seed=20 + act)
+
+
+def test_alpha_residual():
+    _run(4, 512, 256, 5, -1, act=5, use_bias=True, use_res=True, alpha=0.5, seed=31)
+    _run(8, 512, 256, 1, 128, use_res=True, seed=32)
+
+
+@pytest.mark.parametrize("K,N", [(3584, 4608), (3584, 3584), (3584, 18944), (18944, 3584)])
+@pytest.mark.parametrize("M", [1, 8])
+def test_qwen2_7b_projections_w4(K, N, M):
+    _run(4, K, N, M, -1, use_bias=(N == 4608), seed=K % 97 + M)
+
+
+def test_qwen2_7b_w8_and_g128():
+    _run(8, 3584, 3584, 1, -1, seed=41)
+    _run(4, 4096, 6144, 32, 128, seed=42)  # Llama-3-8B QKV, GPTQ g128, batch 32
+
+
+def test_forced_split_paths(monkeypatch):
+    monkeypatch.setenv("B2_GEMM_FORCE_SPLIT", "1")
+    _run(4, 1024, 256, 2, -1, seed=51)
+    monkeypatch.setenv("B2_GEMM_FORCE_SPLIT", "7")
+    _run(4, 1024, 256, 2, -1, seed=52)
+    _run(8, 1024, 256, 9, 128, seed=53)
+
+
+def test_linearity_full_size():
+    """Size-independent property at a full-size projection: f(a1 + a2) == f(a1) + f(a2) within bf16 rounding,
+    and f(0) == bias exactly."""
+    from b200spark import ops, quantize as PQ
+    K, N = 3584, 18944
+    g = torch.Generator().manual_seed(5)
+    w = (torch.randn(K, N, generator=g) * 0.02).to(torch.bfloat16)
+    qd, s, z = PQ.quantize_a16w4(w.cuda(), -1)
+    op = ops.GemmWQ(K, N, 4, -1, max_m=8).prepare(qd, s, z)
+    ws = ops.Workspace()
+    a1 = (torch.rand(4, K, generator=g) - 0.5).to(torch.bfloat16).cuda()
+    a2 = torch.zeros_like(a1)
+    a2[:, ::2] = 0.25
+    s12 = (a1.float() + a2.float()).to(torch.bfloat16)
+    exact = (s12.float() == a1.float() + a2.float()).all().item()
+    y1, y2, y12 = op(a1, ws).float(), op(a2, ws).float(), op(s12, ws).float()
+    y0 = op(torch.zeros_like(a1), ws).float()
+    assert torch.count_nonzero(y0) == 0
+    if exact:
+        assert (y12 - (y1 + y2)).abs().max().item() <= 2e-2 * max(1.0, y12.abs().max().item())
