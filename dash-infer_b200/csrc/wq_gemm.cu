@@ -521,7 +521,7 @@ static int make_plan(b2_gemm_wq* h, int mti) {
   };
   // first guess occupancy with the cap, derive S, then shrink xt to what a unit really needs
   int smem = smem_for(xt_cap);
-  B2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin()));
+  B2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int occ = 1;
   B2_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
   if (occ < 1) occ = 1;
