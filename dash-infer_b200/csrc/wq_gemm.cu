@@ -48,8 +48,8 @@ struct GemmParams {
   int M, N, K, Np, KT, NG, S;
   int group_tiles;  // k-tiles per quant group (GROUPED) else 0
   int quanta;       // number of split quanta (KT / max(group_tiles,1))
-  int xt;           // k-tiles per activation chunk
-  int nstage;
+  int xt;           // k-tiles per activation chunk (multiple of TPS and of the quant group)
+  int nst_log2;     // log2(pipeline stages)
   int act;
   float alpha;
 };
@@ -65,10 +65,76 @@ struct WTraits {
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
+// One k-tile (64 k x 16 n per warp) of tensor-core work for this warp.  All addressing is precomputed by the caller.
+template <int WBITS, int MT>
+__device__ __forceinline__ void tile_mma(float (&acc)[MT][4], float (&acch)[MT][4], uint32_t waddr, uint32_t xaddr, int XS8) {
+  uint4 xb[MT][2];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+    xb[m][0] = lds128(xaddr + m * XS8);
+    xb[m][1] = lds128(xaddr + m * XS8 + 16);
+  }
+  if (WBITS == 4) {
+    const uint4 wv = lds128(waddr);
+    const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t w = ww[j];
+      const uint32_t a0 = lop3_and_or(w, kMask4, kMagic);
+      const uint32_t a1 = lop3_and_or(__funnelshift_r(w, w, 4), kMask4, kMagic);
+      const uint32_t a2 = lop3_and_or(__funnelshift_r(w, w, 8), kMask4, kMagic);
+      const uint32_t a3 = lop3_and_or(__funnelshift_r(w, w, 12), kMask4, kMagic);
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const uint32_t b0 = (j & 1) ? ((j & 2) ? xb[m][1].z : xb[m][0].z) : ((j & 2) ? xb[m][1].x : xb[m][0].x);
+        const uint32_t b1 = (j & 1) ? ((j & 2) ? xb[m][1].w : xb[m][0].w) : ((j & 2) ? xb[m][1].y : xb[m][0].y);
+        mma_bf16_16816(acc[m], a0, a1, a2, a3, b0, b1);
+      }
+    }
+  } else if (WBITS == 8) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const uint4 wv = lds128(waddr + c * 512);
+      const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const uint32_t wa = ww[2 * jj], wb = ww[2 * jj + 1];
+        const uint32_t l0 = lop3_and_or(wa, kMask4, kMagic);
+        const uint32_t h0 = lop3_and_or(__funnelshift_r(wa, wa, 4), kMask4, kMagic);
+        const uint32_t l1 = lop3_and_or(__funnelshift_r(wa, wa, 8), kMask4, kMagic);
+        const uint32_t h1 = lop3_and_or(__funnelshift_r(wa, wa, 12), kMask4, kMagic);
+        const uint32_t l2 = lop3_and_or(wb, kMask4, kMagic);
+        const uint32_t h2 = lop3_and_or(__funnelshift_r(wb, wb, 4), kMask4, kMagic);
+        const uint32_t l3 = lop3_and_or(__funnelshift_r(wb, wb, 8), kMask4, kMagic);
+        const uint32_t h3 = lop3_and_or(__funnelshift_r(wb, wb, 12), kMask4, kMagic);
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          const uint32_t b0 = jj ? xb[m][c].z : xb[m][c].x;
+          const uint32_t b1 = jj ? xb[m][c].w : xb[m][c].y;
+          mma_bf16_16816(acc[m], l0, l1, l2, l3, b0, b1);
+          mma_bf16_16816(acch[m], h0, h1, h2, h3, b0, b1);
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 wv = lds128(waddr + j * 512);
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const uint32_t b0 = (j & 1) ? xb[m][j >> 1].z : xb[m][j >> 1].x;
+        const uint32_t b1 = (j & 1) ? xb[m][j >> 1].w : xb[m][j >> 1].y;
+        mma_bf16_16816(acc[m], wv.x, wv.y, wv.z, wv.w, b0, b1);
+      }
+    }
+  }
+}
+
 template <int WBITS, int MT, bool GROUPED>
 __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
   using T = WTraits<WBITS>;
   constexpr int MP = 8 * MT;
+  const int NST = 1 << p.nst_log2;
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -83,19 +149,18 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
 
   // ---- shared memory carve-up
   uint8_t* ring = smem;
-  const int ring_bytes = p.nstage * T::STAGE_BYTES;
+  const int ring_bytes = NST * T::STAGE_BYTES;
   const int XS = p.xt * 128 + 16;  // activation row stride (bytes), == 16 mod 128: conflict-free LDS.128
   uint8_t* xs = ring + ring_bytes;
   float* fs = reinterpret_cast<float*>(xs + MP * XS);        // [MP][kBN] partial tile
   float* suma = fs + MP * kBN;                                // [MP][groups per chunk] (or [MP])
   const int gpc = GROUPED ? p.xt / gt : 1;                    // groups per chunk
-  uint64_t* full = reinterpret_cast<uint64_t*>(suma + MP * (gpc > 0 ? gpc : 1) + 4);
-  full = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(full) + 7) & ~uintptr_t(7));
-  uint64_t* empty = full + p.nstage;
+  uint64_t* full = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(suma + MP * gpc + 4) + 7) & ~uintptr_t(7));
+  uint64_t* empty = full + NST;
   __shared__ int s_is_last;
 
   if (tid == 0) {
-    for (int i = 0; i < p.nstage; ++i) {
+    for (int i = 0; i < NST; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], kWarps);
     }
@@ -104,15 +169,14 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
   __syncthreads();
   pdl_launch_dependents();  // let the next kernel start streaming ITS weights as soon as SM resources free up
 
-  const uint8_t* wsrc = p.packed + ((size_t)ng * p.KT + kt0) * T::TILE_BYTES;
-  const int nstages_total = (nt + T::TPS - 1) / T::TPS;
-
   if (warp == kWarps) {
     // ===================== producer: TMA bulk copies, independent of the previous kernel ==========
     if (lane == 0) {
+      const uint8_t* wsrc = p.packed + ((size_t)ng * p.KT + kt0) * T::TILE_BYTES;
+      const int nstages_total = (nt + T::TPS - 1) / T::TPS;
       for (int i = 0; i < nstages_total; ++i) {
-        const int slot = i % p.nstage, use = i / p.nstage;
-        mbar_wait(&empty[slot], (use & 1) ^ 1);
+        const int slot = i & (NST - 1);
+        if (i >= NST) mbar_wait(&empty[slot], ((i >> p.nst_log2) & 1) ^ 1);
         const int tiles = min(T::TPS, nt - i * T::TPS);
         const uint32_t bytes = tiles * T::TILE_BYTES;
         mbar_arrive_expect_tx(&full[slot], bytes);
@@ -138,146 +202,78 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
 
   pdl_wait();  // activations / workspace / counters belong to the previous kernels from here on
 
-  const uint32_t ring_u32 = smem_u32(ring);
-  const uint32_t xs_u32 = smem_u32(xs);
-  const int ctid = tid;  // 0..255 among consumers
-  int tile_i = 0;        // tile index within the unit
+  const uint32_t w_thr = smem_u32(ring) + warp * (32 * T::LB) + lane * 16;
+  const uint32_t x_thr = smem_u32(xs) + g * XS + t * 32;
+  const int XS8 = 8 * XS;
+  int stage_i = 0;
 
-  for (int xc0 = 0; xc0 < nt; xc0 += p.xt) {
+  for (int xc0 = 0; xc0 < nt; xc0 += p.xt) {  // p.xt is a multiple of TPS and of the quant group
     const int xn = min(p.xt, nt - xc0);
-    named_bar_sync(1, kWarps * 32);  // previous chunk fully consumed
-    // ---- stage activations A[m][k-chunk] (bf16) -> xs, zero-filling m >= M and k >= K
+    if (xc0 > 0) named_bar_sync(1, kWarps * 32);  // previous chunk fully consumed
+    // ---- stage activations A[m][k-chunk] (bf16) -> xs (zero-fill m >= M, k >= K) and, in the same pass,
+    //      sum_k a[m][k] per (row, quant group): the zero-point term of the affine dequant
     {
-      const int vec_per_row = xn * 8;  // 16B vectors
       const int64_t kbase = (int64_t)(kt0 + xc0) * kBK;
-      for (int idx = ctid; idx < MP * vec_per_row; idx += kWarps * 32) {
-        const int m = idx / vec_per_row, v = idx - m * vec_per_row;
-        const int64_t k = kbase + v * 8;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (m < p.M && k < p.K) val = *reinterpret_cast<const uint4*>(p.A + (int64_t)m * p.lda + k);
-        *reinterpret_cast<uint4*>(xs + m * XS + v * 16) = val;
-      }
-    }
-    named_bar_sync(1, kWarps * 32);
-    // ---- sum_k a[m][k] per (row, quant group) of this chunk — the zero-point term
-    {
-      const int ngroups = GROUPED ? xn / gt : 1;
-      const int vec_per_group = (GROUPED ? gt : xn) * 8;
-      for (int job = warp; job < MP * ngroups; job += kWarps) {
-        const int m = job / ngroups, gi = job - m * ngroups;
-        float sacc = 0.f;
-        for (int v = lane; v < vec_per_group; v += 32) {
-          const uint4 val = *reinterpret_cast<const uint4*>(xs + m * XS + (gi * vec_per_group + v) * 16);
-          sacc += bf16_lo(val.x) + bf16_hi(val.x) + bf16_lo(val.y) + bf16_hi(val.y) + bf16_lo(val.z) +
-                  bf16_hi(val.z) + bf16_lo(val.w) + bf16_hi(val.w);
-        }
+      const int nvec = xn * 8;
+      const int gvec = GROUPED ? gt * 8 : nvec;  // 16B vectors per quant group
+      for (int m = warp; m < MP; m += kWarps) {
+        const __nv_bfloat16* arow = p.A + (int64_t)m * p.lda + kbase;
+        uint8_t* xrow = xs + m * XS;
+        const bool mrow = m < p.M;
+        for (int v0 = 0, gi = 0; v0 < nvec; v0 += gvec, ++gi) {
+          float sacc = 0.f;
+          for (int v = v0 + lane; v < v0 + gvec; v += 32) {
+            uint4 val = make_uint4(0, 0, 0, 0);
+            if (mrow && kbase + v * 8 < p.K) val = *reinterpret_cast<const uint4*>(arow + v * 8);
+            *reinterpret_cast<uint4*>(xrow + v * 16) = val;
+            sacc += (bf16_lo(val.x) + bf16_hi(val.x)) + (bf16_lo(val.y) + bf16_hi(val.y)) +
+                    (bf16_lo(val.z) + bf16_hi(val.z)) + (bf16_lo(val.w) + bf16_hi(val.w));
+          }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
-        if (lane == 0) {
-          if (GROUPED) suma[m * gpc + gi] = sacc;
-          else suma[m] = (xc0 == 0 ? 0.f : suma[m]) + sacc;
-        }
-      }
-    }
-    named_bar_sync(1, kWarps * 32);
-
-    // ---- main loop over the k-tiles of this chunk
-    for (int xt_i = 0; xt_i < xn; ++xt_i, ++tile_i) {
-      const int stage_i = tile_i / T::TPS, in_stage = tile_i - stage_i * T::TPS;
-      const int slot = stage_i % p.nstage, use = stage_i / p.nstage;
-      if (in_stage == 0) mbar_wait(&full[slot], use & 1);
-
-      if (GROUPED && (xt_i % gt) == 0) {  // prefetch this group's (scale, zero) — consumed at group end
-        const int grp = (kt0 + xc0 + xt_i) / gt;
-        sz0 = p.sz[(size_t)grp * p.Np + n0];
-        sz1 = p.sz[(size_t)grp * p.Np + n0 + 8];
-      }
-
-      // activation (B) fragments: this thread's 16 consecutive k of the tile, for each m8 block
-      uint4 xb[MT][2];
-#pragma unroll
-      for (int m = 0; m < MT; ++m) {
-        const uint32_t a = xs_u32 + (m * 8 + g) * XS + xt_i * 128 + t * 32;
-        xb[m][0] = lds128(a);
-        xb[m][1] = lds128(a + 16);
-      }
-      const uint32_t wbase = ring_u32 + slot * T::STAGE_BYTES + in_stage * T::TILE_BYTES + warp * (32 * T::LB) + lane * 16;
-
-      if (WBITS == 4) {
-        const uint4 wv = lds128(wbase);
-        const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t w = ww[j];
-          const uint32_t a0 = lop3_and_or(w, kMask4, kMagic);
-          const uint32_t a1 = lop3_and_or(__funnelshift_r(w, w, 4), kMask4, kMagic);
-          const uint32_t a2 = lop3_and_or(__funnelshift_r(w, w, 8), kMask4, kMagic);
-          const uint32_t a3 = lop3_and_or(__funnelshift_r(w, w, 12), kMask4, kMagic);
-#pragma unroll
-          for (int m = 0; m < MT; ++m) {
-            const uint32_t b0 = (j & 1) ? ((j & 2) ? xb[m][1].z : xb[m][0].z) : ((j & 2) ? xb[m][1].x : xb[m][0].x);
-            const uint32_t b1 = (j & 1) ? ((j & 2) ? xb[m][1].w : xb[m][0].w) : ((j & 2) ? xb[m][1].y : xb[m][0].y);
-            mma_bf16_16816(acc[m], a0, a1, a2, a3, b0, b1);
+          for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+          if (lane == 0) {
+            if (GROUPED) suma[m * gpc + gi] = sacc;
+            else suma[m] = (xc0 == 0 ? 0.f : suma[m]) + sacc;
           }
         }
-      } else if (WBITS == 8) {
+      }
+    }
+    named_bar_sync(1, kWarps * 32);
+
+    // ---- main loop: one pipeline stage (TPS k-tiles) per iteration
+    int gcount = 0;  // tiles into the current quant group
+    for (int xs0 = 0; xs0 < xn; xs0 += T::TPS, ++stage_i) {
+      const int slot = stage_i & (NST - 1);
+      mbar_wait(&full[slot], (stage_i >> p.nst_log2) & 1);
+      const uint32_t wst = w_thr + slot * T::STAGE_BYTES;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const uint4 wv = lds128(wbase + c * 512);
-          const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+      for (int ti = 0; ti < T::TPS; ++ti) {
+        if (T::TPS > 1 && xs0 + ti >= xn) break;
+        if (GROUPED && gcount == 0) {  // prefetch this group's (scale, zero) — consumed at group end
+          const int grp = (kt0 + xc0 + xs0 + ti) / gt;
+          sz0 = p.sz[(size_t)grp * p.Np + n0];
+          sz1 = p.sz[(size_t)grp * p.Np + n0 + 8];
+        }
+        tile_mma<WBITS, MT>(acc, acch, wst + ti * T::TILE_BYTES, x_thr + (xs0 + ti) * 128, XS8);
+        if (GROUPED && ++gcount == gt) {  // fold this quant group into the fp32 result
+          gcount = 0;
+          const int gi = (xs0 + ti) / gt;
 #pragma unroll
-          for (int jj = 0; jj < 2; ++jj) {
-            const uint32_t wa = ww[2 * jj], wb = ww[2 * jj + 1];
-            const uint32_t l0 = lop3_and_or(wa, kMask4, kMagic);
-            const uint32_t h0 = lop3_and_or(__funnelshift_r(wa, wa, 4), kMask4, kMagic);
-            const uint32_t l1 = lop3_and_or(__funnelshift_r(wa, wa, 8), kMask4, kMagic);
-            const uint32_t h1 = lop3_and_or(__funnelshift_r(wa, wa, 12), kMask4, kMagic);
-            const uint32_t l2 = lop3_and_or(wb, kMask4, kMagic);
-            const uint32_t h2 = lop3_and_or(__funnelshift_r(wb, wb, 4), kMask4, kMagic);
-            const uint32_t l3 = lop3_and_or(__funnelshift_r(wb, wb, 8), kMask4, kMagic);
-            const uint32_t h3 = lop3_and_or(__funnelshift_r(wb, wb, 12), kMask4, kMagic);
+          for (int m = 0; m < MT; ++m) {
 #pragma unroll
-            for (int m = 0; m < MT; ++m) {
-              const uint32_t b0 = jj ? xb[m][c].z : xb[m][c].x;
-              const uint32_t b1 = jj ? xb[m][c].w : xb[m][c].y;
-              mma_bf16_16816(acc[m], l0, l1, l2, l3, b0, b1);
-              mma_bf16_16816(acch[m], h0, h1, h2, h3, b0, b1);
+            for (int c = 0; c < 4; ++c) {
+              const float2 z = (c < 2) ? sz0 : sz1;
+              const float sa = suma[(m * 8 + 2 * t + (c & 1)) * gpc + gi];
+              const float raw = (WBITS == 8) ? (16.f * acch[m][c] + acc[m][c]) : acc[m][c];
+              facc[m][c] += z.x * (raw - z.y * sa);
+              acc[m][c] = 0.f;
+              acch[m][c] = 0.f;
             }
           }
         }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint4 wv = lds128(wbase + j * 512);
-#pragma unroll
-          for (int m = 0; m < MT; ++m) {
-            const uint32_t b0 = (j & 1) ? xb[m][j >> 1].z : xb[m][j >> 1].x;
-            const uint32_t b1 = (j & 1) ? xb[m][j >> 1].w : xb[m][j >> 1].y;
-            mma_bf16_16816(acc[m], wv.x, wv.y, wv.z, wv.w, b0, b1);
-          }
-        }
       }
-
-      if (in_stage == T::TPS - 1 || tile_i == nt - 1) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[slot]);
-      }
-
-      if (GROUPED && ((xt_i + 1) % gt) == 0) {  // fold this quant group into the fp32 result
-        const int gi = xt_i / gt;
-#pragma unroll
-        for (int m = 0; m < MT; ++m) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const float2 z = (c < 2) ? sz0 : sz1;
-            const float sa = suma[(m * 8 + 2 * t + (c & 1)) * gpc + gi];
-            const float raw = (WBITS == 8) ? (16.f * acch[m][c] + acc[m][c]) : acc[m][c];
-            facc[m][c] += z.x * (raw - z.y * sa);
-            acc[m][c] = 0.f;
-            acch[m][c] = 0.f;
-          }
-        }
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[slot]);
     }
   }
 
@@ -300,6 +296,7 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
   }
   named_bar_sync(1, kWarps * 32);
 
+  const int ctid = tid;
   const int MPK = MP * kBN;
   if (p.S > 1) {
     float* wsu = p.ws + ((size_t)ng * p.S + s) * MPK;
@@ -314,13 +311,19 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
     named_bar_sync(1, kWarps * 32);
     if (!s_is_last) return;
     __threadfence();
-    // fixed-order sum over the S partials (deterministic)
+    // fixed-order sum over the S partials (deterministic); loads are issued 8 at a time so the L2 round
+    // trips overlap instead of serialising behind the adds
     const float* wsg = p.ws + (size_t)ng * p.S * MPK;
     for (int i = ctid * 4; i < p.M * kBN; i += kWarps * 32 * 4) {
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int ss = 0; ss < p.S; ++ss) {
-        const float4 b = __ldcg(reinterpret_cast<const float4*>(wsg + (size_t)ss * MPK + i));
-        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      for (int s0 = 0; s0 < p.S; s0 += 8) {
+        float4 b[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          b[u] = (s0 + u < p.S) ? __ldcg(reinterpret_cast<const float4*>(wsg + (size_t)(s0 + u) * MPK + i))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { a.x += b[u].x; a.y += b[u].y; a.z += b[u].z; a.w += b[u].w; }
       }
       *reinterpret_cast<float4*>(fs + i) = a;
     }
@@ -330,7 +333,7 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
 
   // ---- final: alpha, bias, activation, residual, bf16 store (coalesced along n)
   for (int i = ctid; i < p.M * (kBN / 2); i += kWarps * 32) {
-    const int m = i / (kBN / 2), np = i - m * (kBN / 2);
+    const int m = i >> 6, np = i & 63;
     const int n = ng * kBN + np * 2;
     if (n >= p.N) continue;
     float v0 = fs[m * kBN + np * 2] * p.alpha, v1 = fs[m * kBN + np * 2 + 1] * p.alpha;
@@ -461,7 +464,7 @@ using namespace b2;
 
 struct Plan {
   bool valid = false;
-  int S = 1, xt = 1, nstage = 4, smem = 0, quanta = 1;
+  int S = 1, xt = 1, smem = 0, quanta = 1, nst_log2 = 2;
 };
 
 struct b2_gemm_wq {
@@ -509,12 +512,17 @@ static int make_plan(b2_gemm_wq* h, int mti) {
   const int quanta = h->KT / gt;
   const int sms = sm_count();
   gemm_kernel_t kern = pick_kernel(h->d.wbits, grouped, mt);
-  const int nstage = env_int("B2_GEMM_STAGES", h->d.wbits == 16 ? 3 : 6);
+  const int ring_kb = env_int("B2_GEMM_RING_KB", 32);
+  int nst_log2 = 1;
+  while ((2 << nst_log2) * stage_bytes_of(h->d.wbits) <= ring_kb * 1024) ++nst_log2;
+  const int nstage = 1 << nst_log2;
+  const int tps = kStageBytes / tile_bytes_of(h->d.wbits) > 0 ? kStageBytes / tile_bytes_of(h->d.wbits) : 1;
+  const int xq = gt > tps ? gt : tps;  // chunk granularity (gt and tps are powers of two)
   const int x_budget = env_int("B2_GEMM_XBYTES", 20 * 1024);
   // activation chunk: as many k-tiles as fit the budget, a multiple of the quant group
   int xt_cap = (x_budget / MP - 16) / 128;
-  xt_cap = xt_cap / gt * gt;
-  if (xt_cap < gt) xt_cap = gt;
+  xt_cap = xt_cap / xq * xq;
+  if (xt_cap < xq) xt_cap = xq;
   auto smem_for = [&](int xt) {
     const int gpc = grouped ? xt / gt : 1;
     return nstage * stage_bytes_of(h->d.wbits) + MP * (xt * 128 + 16) + MP * kBN * 4 + MP * gpc * 4 + 16 + 8 + nstage * 16 + 64;
@@ -525,6 +533,8 @@ static int make_plan(b2_gemm_wq* h, int mti) {
   int occ = 1;
   B2_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
   if (occ < 1) occ = 1;
+  const int want = env_int("B2_GEMM_CTAS_PER_SM", 4);  // leave room for the NEXT kernel's CTAs (PDL overlap)
+  if (want > 0 && occ > want) occ = want;
   const int slots = occ * sms;
   int S = slots / h->NG;
   const int min_quanta = (2 + gt - 1) / gt;  // at least ~2 k-tiles per unit
@@ -536,10 +546,10 @@ static int make_plan(b2_gemm_wq* h, int mti) {
   if (force > 0) S = force < quanta ? force : quanta;
   const int unit_tiles = ((quanta + S - 1) / S) * gt;
   int xt = unit_tiles < xt_cap ? unit_tiles : xt_cap;
-  xt = (xt + gt - 1) / gt * gt;
+  xt = (xt + xq - 1) / xq * xq;
   pl.S = S;
   pl.xt = xt;
-  pl.nstage = nstage;
+  pl.nst_log2 = nst_log2;
   pl.smem = smem_for(xt);
   pl.quanta = quanta;
   pl.valid = true;
@@ -702,7 +712,7 @@ int b2_gemm_wq_run(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, int64_t 
     p.group_tiles = h->group_tiles;
     p.quanta = pl.quanta;
     p.xt = pl.xt;
-    p.nstage = pl.nstage;
+    p.nst_log2 = pl.nst_log2;
     p.act = activation;
     p.alpha = alpha;
     gemm_kernel_t kern = pick_kernel(h->d.wbits, grouped, 1 << mti);

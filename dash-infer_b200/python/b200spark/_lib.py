@@ -85,6 +85,8 @@ def _load():
 
 
 lib = _load()
+if os.environ.get("B2_PDL", "1") == "0":
+    lib.b2_set_pdl(0)
 
 
 def check(status, what=""):

@@ -1,0 +1,188 @@
+"""Decode-step harness: the reference's per-layer operator sequence (python/pyhie/allspark/model/qwen_v15.py:206-379,
+SURVEY.md §1) driven through the b200spark C ABI, with synthetic weights and CUDA-graph replay.
+
+This is measurement/test scaffolding around the hot path (the reference's AsModel::GenerateContinueDecoder loop,
+csrc/core/model/model.cpp:1212-1323, stays the real caller); it owns no numerics of its own: every tensor op is a
+library kernel.
+
+Graph per layer (reference order, with the fusions the C ABI offers):
+  RMSNorm -> GemmA16Wx(QKV,+bias) -> [Rotary + cache append + Q gather] -> SpanAttention
+  -> GemmA16Wx(o_proj) (+residual) -> RMSNorm -> GemmA16Wx(gate, SiLU) -> GemmA16Wx(up) -> MUL
+  -> GemmA16Wx(down) (+residual);  final RMSNorm -> Gemm(lm_head, bf16) -> argmax.
+"""
+from dataclasses import dataclass
+
+import torch
+
+from . import ops, quantize as PQ
+from ._lib import ACT_NONE, ACT_SILU, BIN_MUL, KV_I8, KV_NONE, KV_U4
+
+
+@dataclass
+class ModelConfig:
+    name: str
+    hidden: int
+    n_heads: int
+    n_kv: int
+    inter: int
+    layers: int
+    vocab: int
+    head: int = 128
+    rope_base: float = 1e6
+    eps: float = 1e-6
+    qkv_bias: bool = True
+
+
+QWEN2_7B = ModelConfig("Qwen2-7B", 3584, 28, 4, 18944, 28, 152064)
+LLAMA3_8B = ModelConfig("Llama-3-8B", 4096, 32, 8, 14336, 32, 128256, rope_base=5e5, eps=1e-5, qkv_bias=False)
+QWEN2_72B = ModelConfig("Qwen2-72B", 8192, 64, 8, 29568, 80, 152064)
+TINY = ModelConfig("tiny-2L", 512, 8, 2, 1024, 2, 1024)
+
+KV_MODES = {"none": KV_NONE, "bf16": KV_NONE, "i8": KV_I8, "u4": KV_U4}
+
+
+def synth_weight(K, N, gen, device, std=0.02):
+    return (torch.randn(K, N, generator=gen, device=device, dtype=torch.float32) * std).to(torch.bfloat16)
+
+
+class QuantLinear:
+    """One projection: synthetic bf16 weight -> IQ quantizer -> GemmWQ handle (keeps nothing but the handle)."""
+
+    def __init__(self, K, N, wbits, group, gen, device, max_m, bias=False, keep_ref=False):
+        w = synth_weight(K, N, gen, device)
+        b = (torch.randn(N, generator=gen, device=device) * 0.02).to(torch.bfloat16) if bias else None
+        self.K, self.N, self.wbits = K, N, wbits
+        self.op = ops.GemmWQ(K, N, wbits, group, max_m=max_m)
+        if wbits == 4:
+            q, s, z = PQ.quantize_a16w4(w, group)
+        elif wbits == 8:
+            q, s, z = PQ.quantize_a16w8(w, group)
+        else:
+            q, s, z = w, None, None
+        self.op.prepare(q, s, z, b)
+        self.ref = None
+        if keep_ref:  # dense fp32 (q - z) * s for the CPU oracle
+            self.ref = (PQ.dequantize(q, s, z, group, wbits, N) if wbits != 16 else w.float()).cpu()
+            self.ref_bias = b.float().cpu() if b is not None else None
+
+    def __call__(self, x, ws, **kw):
+        return self.op(x, ws, **kw)
+
+
+class DecodeStack:
+    def __init__(self, cfg, batch, max_len, wbits=4, group=-1, kv="none", span=128, seed=1234, device="cuda",
+                 keep_ref=False, layers=None):
+        self.cfg, self.B, self.max_len = cfg, batch, max_len
+        self.device = device
+        self.n_layers = layers if layers is not None else cfg.layers
+        self.kv_mode = KV_MODES[kv]
+        gen = torch.Generator(device=device).manual_seed(seed)
+        H, nH, nG, I = cfg.hidden, cfg.n_heads, cfg.n_kv, cfg.inter
+        self.embed = synth_weight(cfg.vocab, H, gen, device, std=1.0)
+        self.layers = []
+        for _ in range(self.n_layers):
+            L = {}
+            L["g1"] = (1.0 + 0.1 * torch.randn(H, generator=gen, device=device)).to(torch.bfloat16)
+            L["qkv"] = QuantLinear(H, (nH + 2 * nG) * 128, wbits, group, gen, device, batch, bias=cfg.qkv_bias, keep_ref=keep_ref)
+            L["o"] = QuantLinear(nH * 128, H, wbits, group, gen, device, batch, keep_ref=keep_ref)
+            L["g2"] = (1.0 + 0.1 * torch.randn(H, generator=gen, device=device)).to(torch.bfloat16)
+            L["gate"] = QuantLinear(H, I, wbits, group, gen, device, batch, keep_ref=keep_ref)
+            L["up"] = QuantLinear(H, I, wbits, group, gen, device, batch, keep_ref=keep_ref)
+            L["down"] = QuantLinear(I, H, wbits, group, gen, device, batch, keep_ref=keep_ref)
+            L["cache"] = ops.SpanCache(batch, max_len, nH, nG, span, self.kv_mode, device)
+            self.layers.append(L)
+        self.gf = (1.0 + 0.1 * torch.randn(H, generator=gen, device=device)).to(torch.bfloat16)
+        self.lm_head = QuantLinear(H, cfg.vocab, 16, -1, gen, device, batch, keep_ref=keep_ref)
+        self.attn = ops.SpanAttn(self.layers[0]["cache"].cfg, batch)
+        self.ws = ops.Workspace(device)
+        self.rope = (cfg.rope_base, 128)
+        # device-resident step state
+        self.lens_old = torch.zeros(batch, dtype=torch.int32, device=device)
+        self.lens_new = torch.ones(batch, dtype=torch.int32, device=device)
+        self.ids = torch.zeros(batch, dtype=torch.int64, device=device)
+        self.next_ids = torch.zeros(batch, dtype=torch.int64, device=device)
+        bf = dict(dtype=torch.bfloat16, device=device)
+        self.x = torch.empty(batch, H, **bf)
+        self.xn = torch.empty(batch, H, **bf)
+        self.qkv = torch.empty(batch, (nH + 2 * nG) * 128, **bf)
+        self.q = torch.empty(batch, nH * 128, **bf)
+        self.ao = torch.empty(batch, nH * 128, **bf)
+        self.gate = torch.empty(batch, I, **bf)
+        self.up = torch.empty(batch, I, **bf)
+        self.logits = torch.empty(batch, cfg.vocab, **bf)
+        self.graph = None
+        self.launches_per_step = 0
+
+    # ------------------------------------------------------------------ cache fill
+    def set_context(self, ctx, seed=4321):
+        """Fill every layer's cache with `ctx` tokens of N(0,1) rows THROUGH the append kernel (so quantized spans carry
+        realistic params), and set the sequence lengths."""
+        cfg = self.cfg
+        gen = torch.Generator(device=self.device).manual_seed(seed)
+        width = (cfg.n_heads + 2 * cfg.n_kv) * 128
+        pos = torch.zeros(self.B, dtype=torch.int32, device=self.device)
+        for t in range(ctx):
+            rows = torch.randn(self.B, width, generator=gen, device=self.device).to(torch.bfloat16)
+            for L in self.layers:
+                ops.cache_append(L["cache"], rows, pos, q_out=self.q)
+            pos += 1
+        self.lens_old.fill_(ctx)
+        self.lens_new.fill_(ctx + 1)
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ one decode step (eager or captured)
+    def _step_ops(self):
+        cfg, ws = self.cfg, self.ws
+        n = 0
+        ops.embedding(self.embed, self.ids, out=self.x); n += 1
+        for L in self.layers:
+            ops.rmsnorm(self.x, L["g1"], cfg.eps, out=self.xn); n += 1
+            L["qkv"](self.xn, ws, out=self.qkv); n += 1
+            ops.cache_append(L["cache"], self.qkv, self.lens_old, q_out=self.q, rope=self.rope); n += 1
+            self.attn(self.q, L["cache"], self.lens_new, self.max_len, ws, out=self.ao); n += 1
+            L["o"](self.ao, ws, out=self.x, residual=self.x); n += 1
+            ops.rmsnorm(self.x, L["g2"], cfg.eps, out=self.xn); n += 1
+            L["gate"](self.xn, ws, out=self.gate, act=ACT_SILU); n += 1
+            L["up"](self.xn, ws, out=self.up); n += 1
+            ops.binary(self.gate, self.up, BIN_MUL, out=self.gate); n += 1
+            L["down"](self.gate, ws, out=self.x, residual=self.x); n += 1
+        ops.rmsnorm(self.x, self.gf, cfg.eps, out=self.xn); n += 1
+        self.lm_head(self.xn, ws, out=self.logits); n += 1
+        ops.argmax(self.logits, out=self.next_ids); n += 1
+        ops.lens_add(self.lens_old, 1); n += 1
+        ops.lens_add(self.lens_new, 1); n += 1
+        mchunks = (self.B + 31) // 32  # the small-M GEMM runs M > 32 in row chunks of 32
+        n += (mchunks - 1) * (5 * len(self.layers) + 1)
+        self.launches_per_step = n
+
+    def step(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step_ops()
+        return self.next_ids
+
+    def capture(self):
+        """Warm up once eagerly (plans, workspace growth), rewind the lengths, then capture one step."""
+        lo, ln = self.lens_old.clone(), self.lens_new.clone()
+        self._step_ops()
+        torch.cuda.synchronize()
+        self.lens_old.copy_(lo); self.lens_new.copy_(ln)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._step_ops()
+        self.lens_old.copy_(lo); self.lens_new.copy_(ln)
+        torch.cuda.synchronize()
+        self.graph = g
+        return g
+
+    # ------------------------------------------------------------------ accounting
+    def algo_bytes_per_step(self, ctx):
+        """quantized projection weights + params + bf16 lm_head + KV of every sequence."""
+        wbytes = 0
+        for L in self.layers:
+            for k in ("qkv", "o", "gate", "up", "down"):
+                wbytes += L[k].op.algo_bytes(0)
+        wbytes += self.lm_head.op.algo_bytes(0)
+        kv = self.attn.algo_bytes(self.B * (ctx + 1)) * len(self.layers)
+        return wbytes, kv
