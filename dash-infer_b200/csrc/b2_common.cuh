@@ -112,6 +112,12 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   return v;
 }
 
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+
 // ---- streaming global loads (read-once data: bypass L1 allocation)
 __device__ __forceinline__ uint4 ldg_stream128(const void* p) {
   uint4 v;

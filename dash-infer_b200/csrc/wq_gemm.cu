@@ -23,16 +23,14 @@
 #include <new>
 
 #include "b2_common.cuh"
+#include "wq_gemm_shared.cuh"
 
 namespace b2 {
 
 constexpr int kWarps = 8;                  // consumer warps per CTA
 constexpr int kThreads = kWarps * 32 + 32; // + producer warp
-constexpr int kBN = kWarps * 16;           // n per CTA
-constexpr int kBK = 64;                    // k per tile
 constexpr int kStageBytes = 8192;
-constexpr uint32_t kMask4 = 0x00780078u;   // nibble at mantissa bits 3..6 of each bf16 half
-constexpr uint32_t kMagic = 0x41804180u;   // bf16 16.0 in both halves: 16 + q exactly
+static_assert(kBN == kWarps * 16, "one n16 tile per consumer warp");
 
 struct GemmParams {
   const uint8_t* packed;
@@ -65,9 +63,11 @@ struct WTraits {
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-// One k-tile (64 k x 16 n per warp) of tensor-core work for this warp.  All addressing is precomputed by the caller.
+// One k-tile (64 k x 16 n per warp) of tensor-core work for this warp.  woff0/woff1: byte offsets of this thread's
+// row g / row g+8 data inside the tile; xaddr: this thread's 32 bytes of activations (16 consecutive k).
 template <int WBITS, int MT>
-__device__ __forceinline__ void tile_mma(float (&acc)[MT][4], float (&acch)[MT][4], uint32_t waddr, uint32_t xaddr, int XS8) {
+__device__ __forceinline__ void tile_mma(float (&acc)[MT][4], uint32_t wtile, uint32_t woff0, uint32_t woff1, uint32_t xaddr,
+                                         int XS8) {
   uint4 xb[MT][2];
 #pragma unroll
   for (int m = 0; m < MT; ++m) {
@@ -75,56 +75,47 @@ __device__ __forceinline__ void tile_mma(float (&acc)[MT][4], float (&acch)[MT][
     xb[m][1] = lds128(xaddr + m * XS8 + 16);
   }
   if (WBITS == 4) {
-    const uint4 wv = lds128(waddr);
-    const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+    const uint2 w0 = lds64(wtile + woff0), w1 = lds64(wtile + woff1);
+    const uint32_t r0w[2] = {w0.x, w0.y}, r1w[2] = {w1.x, w1.y};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint32_t w = ww[j];
-      const uint32_t a0 = lop3_and_or(w, kMask4, kMagic);
-      const uint32_t a1 = lop3_and_or(__funnelshift_r(w, w, 4), kMask4, kMagic);
-      const uint32_t a2 = lop3_and_or(__funnelshift_r(w, w, 8), kMask4, kMagic);
-      const uint32_t a3 = lop3_and_or(__funnelshift_r(w, w, 12), kMask4, kMagic);
+    for (int j = 0; j < 2; ++j) {
+      const uint32_t u = r0w[j], v = r1w[j];
+      const uint32_t p0 = lop3_and_or(u, kMask4, kMagic), q0 = lop3_and_or(v, kMask4, kMagic);
+      const uint32_t p1 = lop3_and_or(__funnelshift_r(u, u, 4), kMask4, kMagic), q1 = lop3_and_or(__funnelshift_r(v, v, 4), kMask4, kMagic);
+      const uint32_t p2 = lop3_and_or(__funnelshift_r(u, u, 8), kMask4, kMagic), q2 = lop3_and_or(__funnelshift_r(v, v, 8), kMask4, kMagic);
+      const uint32_t p3 = lop3_and_or(__funnelshift_r(u, u, 12), kMask4, kMagic), q3 = lop3_and_or(__funnelshift_r(v, v, 12), kMask4, kMagic);
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
-        const uint32_t b0 = (j & 1) ? ((j & 2) ? xb[m][1].z : xb[m][0].z) : ((j & 2) ? xb[m][1].x : xb[m][0].x);
-        const uint32_t b1 = (j & 1) ? ((j & 2) ? xb[m][1].w : xb[m][0].w) : ((j & 2) ? xb[m][1].y : xb[m][0].y);
-        mma_bf16_16816(acc[m], a0, a1, a2, a3, b0, b1);
+        mma_bf16_16816(acc[m], p0, q0, p1, q1, xb[m][j].x, xb[m][j].y);
+        mma_bf16_16816(acc[m], p2, q2, p3, q3, xb[m][j].z, xb[m][j].w);
       }
     }
   } else if (WBITS == 8) {
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const uint4 wv = lds128(waddr + c * 512);
-      const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        const uint32_t wa = ww[2 * jj], wb = ww[2 * jj + 1];
-        const uint32_t l0 = lop3_and_or(wa, kMask4, kMagic);
-        const uint32_t h0 = lop3_and_or(__funnelshift_r(wa, wa, 4), kMask4, kMagic);
-        const uint32_t l1 = lop3_and_or(__funnelshift_r(wa, wa, 8), kMask4, kMagic);
-        const uint32_t h1 = lop3_and_or(__funnelshift_r(wa, wa, 12), kMask4, kMagic);
-        const uint32_t l2 = lop3_and_or(wb, kMask4, kMagic);
-        const uint32_t h2 = lop3_and_or(__funnelshift_r(wb, wb, 4), kMask4, kMagic);
-        const uint32_t l3 = lop3_and_or(__funnelshift_r(wb, wb, 8), kMask4, kMagic);
-        const uint32_t h3 = lop3_and_or(__funnelshift_r(wb, wb, 12), kMask4, kMagic);
-#pragma unroll
-        for (int m = 0; m < MT; ++m) {
-          const uint32_t b0 = jj ? xb[m][c].z : xb[m][c].x;
-          const uint32_t b1 = jj ? xb[m][c].w : xb[m][c].y;
-          mma_bf16_16816(acc[m], l0, l1, l2, l3, b0, b1);
-          mma_bf16_16816(acch[m], h0, h1, h2, h3, b0, b1);
-        }
-      }
-    }
-  } else {
+    const uint4 w0 = lds128(wtile + woff0), w1 = lds128(wtile + woff1);
+    const uint32_t r0w[4] = {w0.x, w0.y, w0.z, w0.w}, r1w[4] = {w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint4 wv = lds128(waddr + j * 512);
+      const uint32_t u = r0w[j], v = r1w[j];
+      const uint32_t l0 = lop3_and_or(u, kMask4, kMagic), m0 = lop3_and_or(v, kMask4, kMagic);
+      const uint32_t h0 = lop3_and_or(__funnelshift_r(u, u, 4), kMask4, kMagicHi), n0 = lop3_and_or(__funnelshift_r(v, v, 4), kMask4, kMagicHi);
+      const uint32_t l1 = lop3_and_or(__funnelshift_r(u, u, 8), kMask4, kMagic), m1 = lop3_and_or(__funnelshift_r(v, v, 8), kMask4, kMagic);
+      const uint32_t h1 = lop3_and_or(__funnelshift_r(u, u, 12), kMask4, kMagicHi), n1 = lop3_and_or(__funnelshift_r(v, v, 12), kMask4, kMagicHi);
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
         const uint32_t b0 = (j & 1) ? xb[m][j >> 1].z : xb[m][j >> 1].x;
         const uint32_t b1 = (j & 1) ? xb[m][j >> 1].w : xb[m][j >> 1].y;
-        mma_bf16_16816(acc[m], wv.x, wv.y, wv.z, wv.w, b0, b1);
+        mma_bf16_16816(acc[m], l0, m0, l1, m1, b0, b1);   // low nibbles:  16 + lo
+        mma_bf16_16816(acc[m], h0, n0, h1, n1, b0, b1);   // high nibbles: 16 * (16 + hi)
+      }
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const uint4 w0 = lds128(wtile + woff0 + u * 2048), w1 = lds128(wtile + woff1 + u * 2048);
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        mma_bf16_16816(acc[m], w0.x, w1.x, w0.y, w1.y, xb[m][u].x, xb[m][u].y);
+        mma_bf16_16816(acc[m], w0.z, w1.z, w0.w, w1.w, xb[m][u].z, xb[m][u].w);
       }
     }
   }
@@ -194,15 +185,20 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
     sz1 = p.sz[n0 + 8];
   }
 
-  float acc[MT][4], acch[MT][4], facc[MT][4];
+  float acc[MT][4], facc[MT][4];
 #pragma unroll
   for (int m = 0; m < MT; ++m)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[m][c] = acch[m][c] = facc[m][c] = 0.f;
+    for (int c = 0; c < 4; ++c) acc[m][c] = facc[m][c] = 0.f;
 
   pdl_wait();  // activations / workspace / counters belong to the previous kernels from here on
 
-  const uint32_t w_thr = smem_u32(ring) + warp * (32 * T::LB) + lane * 16;
+  const uint32_t w_ring = smem_u32(ring);
+  // this thread's rows (16*warp + g, +8) inside the [chunk][row ^ swz][16B] tile image
+  const int wc = WBITS == 4 ? (t >> 1) : (WBITS == 8 ? t : 2 * t);
+  const int wr = warp * 16 + g;
+  const uint32_t woff0 = wc * 2048 + ((wr ^ tile_swz(WBITS, wc)) << 4) + (WBITS == 4 ? 8 * (t & 1) : 0);
+  const uint32_t woff1 = wc * 2048 + (((wr + 8) ^ tile_swz(WBITS, wc)) << 4) + (WBITS == 4 ? 8 * (t & 1) : 0);
   const uint32_t x_thr = smem_u32(xs) + g * XS + t * 32;
   const int XS8 = 8 * XS;
   int stage_i = 0;
@@ -245,7 +241,7 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
     for (int xs0 = 0; xs0 < xn; xs0 += T::TPS, ++stage_i) {
       const int slot = stage_i & (NST - 1);
       mbar_wait(&full[slot], (stage_i >> p.nst_log2) & 1);
-      const uint32_t wst = w_thr + slot * T::STAGE_BYTES;
+      const uint32_t wst = w_ring + slot * T::STAGE_BYTES;
 #pragma unroll
       for (int ti = 0; ti < T::TPS; ++ti) {
         if (T::TPS > 1 && xs0 + ti >= xn) break;
@@ -254,7 +250,7 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
           sz0 = p.sz[(size_t)grp * p.Np + n0];
           sz1 = p.sz[(size_t)grp * p.Np + n0 + 8];
         }
-        tile_mma<WBITS, MT>(acc, acch, wst + ti * T::TILE_BYTES, x_thr + (xs0 + ti) * 128, XS8);
+        tile_mma<WBITS, MT>(acc, wst + ti * T::TILE_BYTES, woff0, woff1, x_thr + (xs0 + ti) * 128, XS8);
         if (GROUPED && ++gcount == gt) {  // fold this quant group into the fp32 result
           gcount = 0;
           const int gi = (xs0 + ti) / gt;
@@ -264,10 +260,8 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
             for (int c = 0; c < 4; ++c) {
               const float2 z = (c < 2) ? sz0 : sz1;
               const float sa = suma[(m * 8 + 2 * t + (c & 1)) * gpc + gi];
-              const float raw = (WBITS == 8) ? (16.f * acch[m][c] + acc[m][c]) : acc[m][c];
-              facc[m][c] += z.x * (raw - z.y * sa);
+              facc[m][c] += z.x * (acc[m][c] - z.y * sa);
               acc[m][c] = 0.f;
-              acch[m][c] = 0.f;
             }
           }
         }
@@ -288,8 +282,7 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
       else {
         const float2 z = (c < 2) ? sz0 : sz1;
         const float sa = suma[m * 8 + 2 * t + (c & 1)];
-        const float raw = (WBITS == 8) ? (16.f * acch[m][c] + acc[m][c]) : acc[m][c];
-        v = z.x * (raw - z.y * sa);
+        v = z.x * (acc[m][c] - z.y * sa);
       }
       fs[(m * 8 + 2 * t + (c & 1)) * kBN + warp * 16 + g + (c >> 1) * 8] = v;
     }
@@ -362,56 +355,47 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
 // ------------------------------------------------------------------------------------------------
 // init-time re-layout kernels (reference layouts -> tile image).  One thread per 32-bit word.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void frag_coord(int g, int t, int j, int r, int e, int& dn, int& dk) {
-  dn = g + 8 * (r & 1);
-  dk = 16 * t + 4 * j + 2 * (r >> 1) + e;
-}
-
+// One thread per 32-bit word of the image: word index -> (tile, chunk, stored row, word j) -> logical row/k.
 __global__ void pack_w4_kernel(uint32_t* __restrict__ dst, const uint8_t* __restrict__ q, int K, int N, int KT, int NG) {
-  const int64_t total = (int64_t)NG * KT * kWarps * 32 * 4;
+  const int64_t total = (int64_t)NG * KT * 1024;
   const int npack = (N + 1) / 2;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int j = i & 3;
-    const int lane = (i >> 2) & 31;
-    const int w = (i >> 7) & 7;
+    const int rs = (i >> 2) & 127;
+    const int c = (i >> 9) & 1;
     const int64_t tile = i >> 10;
     const int kt = tile % KT, ng = tile / KT;
-    const int g = lane >> 2, t = lane & 3;
+    const int r = rs ^ tile_swz(4, c);
+    const int n = ng * kBN + r;
     uint32_t word = 0;
-    for (int r = 0; r < 4; ++r)
-      for (int e = 0; e < 2; ++e) {
-        int dn, dk;
-        frag_coord(g, t, j, r, e, dn, dk);
-        const int n = ng * kBN + w * 16 + dn, k = kt * kBK + dk;
-        uint32_t v = 0;
-        if (n < N && k < K) {
-          const uint8_t b = q[(int64_t)k * npack + (n >> 1)];
-          v = (n & 1) ? (b >> 4) : (b & 0xF);
-        }
-        word |= v << (4 * (r + 4 * e));
+    for (int nb = 0; nb < 8; ++nb) {
+      const int k = kt * kBK + 32 * c + 8 * j + 2 * (nb & 3) + (nb >> 2);
+      uint32_t v = 0;
+      if (n < N && k < K) {
+        const uint8_t b = q[(int64_t)k * npack + (n >> 1)];
+        v = (n & 1) ? (b >> 4) : (b & 0xF);
       }
+      word |= v << (4 * nb);
+    }
     dst[i] = (word << 3) | (word >> 29);
   }
 }
 
 __global__ void pack_w8_kernel(uint32_t* __restrict__ dst, const uint8_t* __restrict__ q, int K, int N, int KT, int NG,
                                int is_signed) {
-  const int64_t total = (int64_t)NG * KT * kWarps * 2 * 32 * 4;
+  const int64_t total = (int64_t)NG * KT * 2048;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int x = i & 3;
-    const int lane = (i >> 2) & 31;
-    const int c = (i >> 7) & 1;
-    const int w = (i >> 8) & 7;
+    const int j = i & 3;
+    const int rs = (i >> 2) & 127;
+    const int c = (i >> 9) & 3;
     const int64_t tile = i >> 11;
     const int kt = tile % KT, ng = tile / KT;
-    const int g = lane >> 2, t = lane & 3;
-    const int j = 2 * c + (x >> 1), h = x & 1;
+    const int r = rs ^ tile_swz(8, c);
+    const int n = ng * kBN + r;
     uint32_t word = 0;
     for (int b = 0; b < 4; ++b) {
-      const int r = 2 * h + (b & 1), e = b >> 1;
-      int dn, dk;
-      frag_coord(g, t, j, r, e, dn, dk);
-      const int n = ng * kBN + w * 16 + dn, k = kt * kBK + dk;
+      const int kk = (b == 0) ? 0 : (b == 2 ? 1 : (b == 1 ? 2 : 3));  // bytes (b0,b2,b1,b3) hold k+0,1,2,3
+      const int k = kt * kBK + 16 * c + 4 * j + kk;
       uint32_t v = is_signed ? 0x80u : 0u;
       if (n < N && k < K) v = q[(int64_t)k * N + n] ^ (is_signed ? 0x80u : 0u);
       word |= v << (8 * b);
@@ -421,20 +405,18 @@ __global__ void pack_w8_kernel(uint32_t* __restrict__ dst, const uint8_t* __rest
 }
 
 __global__ void pack_w16_kernel(uint32_t* __restrict__ dst, const uint16_t* __restrict__ wsrc, int K, int N, int KT, int NG) {
-  const int64_t total = (int64_t)NG * KT * kWarps * 4 * 32 * 4;
+  const int64_t total = (int64_t)NG * KT * 4096;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = i & 3;
-    const int lane = (i >> 2) & 31;
-    const int j = (i >> 7) & 3;
-    const int w = (i >> 9) & 7;
+    const int j = i & 3;
+    const int rs = (i >> 2) & 127;
+    const int c = (i >> 9) & 7;
     const int64_t tile = i >> 12;
     const int kt = tile % KT, ng = tile / KT;
-    const int g = lane >> 2, t = lane & 3;
+    const int r = rs ^ tile_swz(16, c);
+    const int n = ng * kBN + r;
     uint32_t word = 0;
     for (int e = 0; e < 2; ++e) {
-      int dn, dk;
-      frag_coord(g, t, j, r, e, dn, dk);
-      const int n = ng * kBN + w * 16 + dn, k = kt * kBK + dk;
+      const int k = kt * kBK + 8 * c + 2 * j + e;
       uint32_t v = 0;
       if (n < N && k < K) v = wsrc[(int64_t)k * N + n];
       word |= v << (16 * e);
@@ -477,6 +459,7 @@ struct b2_gemm_wq {
   bool own_sz = false;
   unsigned* counters = nullptr;
   Plan plans[3];  // MT = 1, 2, 4
+  int tc_S = 0;   // split-K of the tcgen05 path (0 = not planned)
   int device = 0;
 };
 
@@ -662,8 +645,31 @@ int b2_gemm_wq_attach_packed(b2_gemm_wq_t h, const void* packed, const void* sca
 
 static int mt_index_for(int M) { return M <= 8 ? 0 : (M <= 16 ? 1 : 2); }
 
+static bool use_tc(const b2_gemm_wq* h, int M) {
+  static const int min_m = env_int("B2_GEMM_TC_MIN_M", 17);
+  return h->d.wbits != 16 && h->group_tiles == 0 && M >= min_m;
+}
+
+static int make_tc_plan(b2_gemm_wq* h) {
+  if (h->tc_S > 0) return B2_OK;
+  B2_CUDA_TRY(tc_configure(h->d.wbits));
+  const int ctas = env_int("B2_GEMM_TC_CTAS_PER_SM", 2);
+  const int slots = ctas * sm_count();
+  int S = slots / h->NG;
+  if (S > h->KT / 4) S = h->KT / 4;
+  const int smax = env_int("B2_GEMM_MAX_SPLIT", 32);
+  if (S > smax) S = smax;
+  if (S < 1) S = 1;
+  h->tc_S = S;
+  return B2_OK;
+}
+
 size_t b2_gemm_wq_workspace_bytes(b2_gemm_wq_t h, int M) {
   if (!h || M <= 0) return 0;
+  if (use_tc(h, M)) {
+    if (make_tc_plan(h) != B2_OK) return 0;
+    return h->tc_S <= 1 ? 16 : (size_t)h->NG * h->tc_S * kTcMaxM * kBN * sizeof(float) + 16;
+  }
   const int mc = M > 32 ? 32 : M;
   const int mti = mt_index_for(mc);
   if (make_plan(h, mti) != B2_OK) return 0;
@@ -691,6 +697,28 @@ int b2_gemm_wq_run(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, int64_t 
   if (workspace_bytes < b2_gemm_wq_workspace_bytes(h, M)) return B2_ERR_PARAM;
   cudaStream_t stream = (cudaStream_t)stream_;
   const bool grouped = h->group_tiles > 0;
+  if (use_tc(h, M)) {  // decode batches 17..: tcgen05 path, 64 rows per launch
+    if (int st = make_tc_plan(h)) return st;
+    if (h->tc_S > 1 && !workspace) return B2_ERR_PARAM;
+    for (int m0 = 0; m0 < M; m0 += kTcMaxM) {
+      TcLaunch a;
+      a.packed = (const uint8_t*)h->packed; a.sz = h->sz;
+      a.A = (const __nv_bfloat16*)A + (int64_t)m0 * lda; a.lda = lda;
+      a.C = (__nv_bfloat16*)C + (int64_t)m0 * ldc; a.ldc = ldc;
+      a.bias = (const __nv_bfloat16*)bias;
+      a.residual = residual ? (const __nv_bfloat16*)residual + (int64_t)m0 * ldc : nullptr;
+      a.ws = (float*)workspace; a.counters = h->counters;
+      a.M = (M - m0) > kTcMaxM ? kTcMaxM : (M - m0);
+      a.N = h->d.N; a.K = h->d.K; a.Np = h->Np; a.KT = h->KT; a.NG = h->NG; a.S = h->tc_S;
+      a.act = activation; a.alpha = alpha;
+      cudaError_t e = tc_launch(h->d.wbits, a, stream);
+      if (e != cudaSuccess) {
+        set_last_error("wq_gemm_tc launch", e);
+        return B2_ERR_CUDA;
+      }
+    }
+    return B2_OK;
+  }
   for (int m0 = 0; m0 < M; m0 += 32) {
     const int mc = (M - m0) > 32 ? 32 : (M - m0);
     const int mti = mt_index_for(mc);

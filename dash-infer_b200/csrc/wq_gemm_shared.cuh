@@ -1,0 +1,44 @@
+// b200spark — definitions shared by the two weight-only GEMM kernels (mma.sync small-M, tcgen05 medium-M).
+#pragma once
+#include "b2_common.cuh"
+
+namespace b2 {
+
+constexpr int kBN = 128;                   // output channels per CTA tile
+constexpr int kBK = 64;                    // k per tile
+constexpr uint32_t kMask4 = 0x00780078u;   // nibble at mantissa bits 3..6 of each bf16 half
+constexpr uint32_t kMagic = 0x41804180u;   // bf16 16.0 in both halves: 16 + q exactly
+constexpr uint32_t kMagicHi = 0x43804380u; // bf16 256.0: 16 * (16 + q) exactly (hi nibble plane of W8)
+
+// ---- weight image layout (one image serves both kernels) ----
+// tile(ng, kt) = 128 output channels x 64 k, stored as [chunk c][row r ^ swz(c)][16 bytes]:
+//   W4 : 2 chunks, chunk = 32 k of one row as 4 words; word j nibble i <-> k = 32c+8j+2i, nibble i+4 <-> k+1
+//   W8 : 4 chunks, chunk = 16 k of one row as 4 words; word j bytes (b0,b2,b1,b3) <-> k = 16c+4j+(0,1,2,3)
+//   W16: 8 chunks, chunk = 8 k of one row, natural order
+// every word of W4/W8 is rotated left by 3 so that (w >> 4i) & 0x00780078 | magic yields two exact bf16 integers.
+__host__ __device__ __forceinline__ int tile_swz(int wbits, int c) {
+  return wbits == 4 ? 4 * (c & 1) : (wbits == 8 ? 2 * (c & 3) : 2 * ((c >> 1) & 3));
+}
+
+// tcgen05 kernel entry (wq_gemm_tc.cu)
+struct TcLaunch {
+  const uint8_t* packed;
+  const float2* sz;
+  const __nv_bfloat16* A;
+  int64_t lda;
+  __nv_bfloat16* C;
+  int64_t ldc;
+  const __nv_bfloat16* bias;
+  const __nv_bfloat16* residual;
+  float* ws;
+  unsigned* counters;
+  int M, N, K, Np, KT, NG, S;
+  int act;
+  float alpha;
+};
+constexpr int kTcMaxM = 64;  // batch rows per tcgen05 launch
+int tc_smem_bytes(int wbits);
+cudaError_t tc_configure(int wbits);
+cudaError_t tc_launch(int wbits, const TcLaunch& a, cudaStream_t stream);
+
+}  // namespace b2
