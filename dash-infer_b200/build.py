@@ -18,7 +18,7 @@ OBJ = os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CUFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
-           "-Xptxas", "-v" if os.environ.get("B2_PTXAS_V") else "-warn-spills"]
+           "-Xptxas", "-v" if os.environ.get("B2_PTXAS_V") else "-warn-spills"] + os.environ.get("B2_EXTRA_NVCC", "").split()
 
 
 def _stamp(path, extra=""):

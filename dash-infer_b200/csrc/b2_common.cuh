@@ -70,16 +70,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(2000u)  // suspend-time hint (ns): sleep in HW instead of spinning
+      : "r"(smem_u32(bar)), "r"(parity)  // no suspend-time hint: ptxas lowers it to NANOSLEEP polling (measured: +2 us per wait)
       : "memory");
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
+}
+
+// for roles with slack (producers): poll with back-off so the spin does not steal issue slots from the math warps
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(40);
 }
 
 // ---- TMA 1D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)

@@ -653,11 +653,11 @@ static bool use_tc(const b2_gemm_wq* h, int M) {
 static int make_tc_plan(b2_gemm_wq* h) {
   if (h->tc_S > 0) return B2_OK;
   B2_CUDA_TRY(tc_configure(h->d.wbits));
-  const int ctas = env_int("B2_GEMM_TC_CTAS_PER_SM", 2);
+  const int ctas = env_int("B2_GEMM_TC_CTAS_PER_SM", 1);
   const int slots = ctas * sm_count();
   int S = slots / h->NG;
   if (S > h->KT / 4) S = h->KT / 4;
-  const int smax = env_int("B2_GEMM_MAX_SPLIT", 32);
+  const int smax = env_int("B2_GEMM_TC_MAX_SPLIT", 6);
   if (S > smax) S = smax;
   if (S < 1) S = 1;
   h->tc_S = S;

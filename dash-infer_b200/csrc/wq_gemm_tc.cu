@@ -11,14 +11,17 @@
 //   warps 2..5  : dequant — one thread per output channel: LDS.128 -> lop3/shf -> exact bf16 integers (16+q)
 //                 -> tcgen05.st into the A-operand region of TMEM (the dequantized weights never touch shared
 //                 memory: its bandwidth could not carry 2 B/weight at HBM rate)
-//   warps 6..7  : activation tiles (64 k x NM m) via cp.async into the 128B-swizzled K-major UMMA layout, plus
-//                 the per-row sums sum_k a[m][k] needed by the zero-point term
+//   warp 8      : activation tiles (64 k x NM m) by TMA tensor-map loads into the 128B-swizzled K-major UMMA
+//                 layout (out-of-range rows/columns are zero-filled by the TMA unit)
+//   warps 6..7  : per-row sums sum_k a[m][k] needed by the zero-point term, read from the landed tiles
 //   warp 1      : one elected thread issues tcgen05.mma (A from TMEM, B from shared memory, D in TMEM) and
 //                 tcgen05.commit's the pipeline barriers
 //   epilogue    : warps 2..5 read D with tcgen05.ld, apply s * (acc - (16+z) * sum a), split-K partial or final
 //                 alpha/bias/activation/residual, bf16 store.
 //
 // Roofline: HBM-bound up to M ~ 64 (256 FLOP/B ~ the tensor/HBM ridge); report both.
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
+
 #include <cstdlib>
 
 #include "b2_common.cuh"
@@ -26,13 +29,13 @@
 
 namespace b2 {
 
-constexpr int kTcThreads = 256;
+constexpr int kTcThreads = 288;      // warp 0 weights TMA, 1 MMA, 2-5 dequant/epilogue, 6-7 row sums, 8 activation TMA
 constexpr int kTcNM = 64;            // batch columns per MMA (UMMA N)
-constexpr int kTcNSW = 8;            // weight stages
-constexpr int kTcNSX = 4;            // activation stages
+constexpr int kTcNSW = 4;            // weight stages (8 KB each)
+constexpr int kTcNSX = 3;            // {dequantized-A buffer in TMEM, activation slot in smem} stages
 constexpr int kTcXTile = kTcNM * 128;  // bytes: NM rows x 64 k bf16
 constexpr int kTcColsD = 0;          // TMEM columns [0, 64): accumulator
-constexpr int kTcColsA = 64;         // TMEM columns [64, ...): two A buffers (W4: 32 columns each, W8: 64 = lo+hi planes)
+constexpr int kTcColsA = 64;         // TMEM columns [64, 256): three A stages of 64 columns
 constexpr int kTcTmemCols = 256;
 
 // ---- tcgen05 wrappers (forms as in cute/arch/{mma_sm100_umma,copy_sm100,tmem_allocator_sm100}.hpp) ----
@@ -69,6 +72,14 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
       : "memory");
 }
 
+// optional timeline instrumentation (CTA 0 only): compiled in with -DB2_TC_TRACE
+#ifdef B2_TC_TRACE
+__device__ unsigned long long g_tc_trace[8][256];
+#define TC_TRACE(role, idx) do { if (blockIdx.x == 0 && (idx) < 256) g_tc_trace[role][idx] = clock64(); } while (0)
+#else
+#define TC_TRACE(role, idx) do {} while (0)
+#endif
+
 struct TcParams {
   const uint8_t* packed;
   const float2* sz;
@@ -86,23 +97,28 @@ struct TcParams {
 };
 
 template <int WBITS>
-__global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParams p) {
+__global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap amap) {
   constexpr int TILE_BYTES = WBITS == 4 ? 4096 : 8192;
-  constexpr int NCH = WBITS == 4 ? 2 : 4;  // 16B chunks per row per k-tile
-  constexpr int ABUF = WBITS == 4 ? 32 : 64;  // TMEM columns per A buffer
+  constexpr int NCH = WBITS == 4 ? 2 : 4;      // 16B chunks per row per k-tile
+  constexpr int TPS = WBITS == 4 ? 2 : 1;      // k-tiles per pipeline stage (k128 for W4, k64 for W8)
+  constexpr int ACOLS = WBITS == 4 ? 32 : 64;  // TMEM columns of dequantized A per k-tile
+  constexpr int ABUF = ACOLS * TPS;            // per stage (64 columns)
+  constexpr int NAB = kTcNSX;                  // A stages in TMEM == activation stages (one 'ready' barrier per stage)
+  constexpr int WSTAGE = TPS * TILE_BYTES;     // 8 KB
+  constexpr int XSTAGE = TPS * kTcXTile;       // 16 KB / 8 KB
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* xring = smem;                                   // NSX x 8 KB, 1024B aligned (SWIZZLE_128B atoms)
-  uint8_t* wring = xring + kTcNSX * kTcXTile;              // NSW x TILE_BYTES
-  float* suma = reinterpret_cast<float*>(wring + kTcNSW * TILE_BYTES);  // [NM]
+  uint8_t* xring = smem;                                   // NSX x XSTAGE, 1024B aligned (SWIZZLE_128B atoms)
+  uint8_t* wring = xring + kTcNSX * XSTAGE;                // NSW x WSTAGE
+  float* suma = reinterpret_cast<float*>(wring + kTcNSW * WSTAGE);  // [NM]
   uint64_t* bars = reinterpret_cast<uint64_t*>(suma + kTcNM);
-  uint64_t* wfull = bars;
-  uint64_t* wfree = wfull + kTcNSW;
-  uint64_t* xfull = wfree + kTcNSW;
-  uint64_t* xfree = xfull + kTcNSX;
-  uint64_t* afull = xfree + kTcNSX;
-  uint64_t* afree = afull + 2;
-  uint64_t* dfull = afree + 2;
+  uint64_t* wfull = bars;                 // [NSW] weights landed (TMA tx)
+  uint64_t* wfree = wfull + kTcNSW;       // [NSW] dequant warps done with the smem stage (4 arrivals)
+  uint64_t* xfull = wfree + kTcNSW;       // [NSX] activations landed (TMA tx)
+  uint64_t* xsum = xfull + kTcNSX;        // [NSX] row sums done with the stage (2 arrivals)
+  uint64_t* afull = xsum + kTcNSX;        // [NAB] dequantized A stage stored in TMEM (4 arrivals)
+  uint64_t* mdone = afull + NAB;          // [NSX] tensor core done with stage (tcgen05.commit): frees A buffer + X slot
+  uint64_t* dfull = mdone + kTcNSX;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dfull + 1);
   __shared__ int s_is_last;
 
@@ -111,11 +127,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
   const int s = blockIdx.x - ng * p.S;
   const int kt0 = (int)((int64_t)s * p.KT / p.S), kt1 = (int)((int64_t)(s + 1) * p.KT / p.S);
   const int nt = kt1 - kt0;
+  const int nst = (nt + TPS - 1) / TPS;  // pipeline stages of this unit
 
   if (tid == 0) {
     for (int i = 0; i < kTcNSW; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wfree[i], 4); }
-    for (int i = 0; i < kTcNSX; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xfree[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&afull[i], 4); mbar_init(&afree[i], 1); }
+    // xfull: TMA tx (sum warps wait on it); ready: TMA tx + 4 dequant-warp arrivals (the MMA thread waits on it)
+    for (int i = 0; i < kTcNSX; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xsum[i], 2); mbar_init(&mdone[i], 1); mbar_init(&afull[i], 5); }
     mbar_init(dfull, 1);
     fence_mbar_init();
   }
@@ -127,149 +144,178 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (tid == 0) TC_TRACE(7, 4);
   pdl_launch_dependents();
 
+  // Stage st uses weight slot st % NSW, X slot st % NSX, A buffer st % NAB; mdone[st % NSX] is committed once the
+  // tensor core has consumed stage st (NSX is a multiple of NAB, so its phase also tells when the A buffer is free).
   if (warp == 0) {
     // ===================== weight producer (does not wait for the previous kernel) =====================
     if (lane == 0) {
       const uint8_t* wsrc = p.packed + ((size_t)ng * p.KT + kt0) * TILE_BYTES;
-      for (int j = 0; j < nt; ++j) {
-        const int slot = j % kTcNSW;
-        if (j >= kTcNSW) mbar_wait(&wfree[slot], ((j / kTcNSW) & 1) ^ 1);
-        mbar_arrive_expect_tx(&wfull[slot], TILE_BYTES);
-        bulk_g2s(wring + slot * TILE_BYTES, wsrc + (size_t)j * TILE_BYTES, TILE_BYTES, &wfull[slot]);
+      for (int st = 0; st < nst; ++st) {
+        const int slot = st % kTcNSW;
+        if (st >= kTcNSW) mbar_wait_backoff(&wfree[slot], ((st / kTcNSW) & 1) ^ 1);
+        const uint32_t bytes = min(TPS, nt - st * TPS) * TILE_BYTES;
+        mbar_arrive_expect_tx(&wfull[slot], bytes);
+        bulk_g2s(wring + slot * WSTAGE, wsrc + (size_t)st * WSTAGE, bytes, &wfull[slot]);
+        TC_TRACE(0, st);
+      }
+    }
+  } else if (warp == 8) {
+    // ===================== activation producer: TMA tensor-map loads (zero fill outside [M, K]) =====================
+    if (lane == 0) {
+      pdl_wait();  // A is the previous kernel's output
+      for (int st = 0; st < nst; ++st) {
+        const int slot = st % kTcNSX;
+        if (st >= kTcNSX) {
+          const uint32_t par = ((st / kTcNSX) & 1) ^ 1;
+          mbar_wait_backoff(&mdone[slot], par);
+          mbar_wait_backoff(&xsum[slot], par);
+        }
+        const int tiles = min(TPS, nt - st * TPS);
+        // the loads complete on the stage's 'ready' barrier (what the MMA thread waits for, together with the dequant
+        // arrivals); the row-sum warps wait on the same barrier phase
+        mbar_arrive_expect_tx(&afull[slot], tiles * kTcXTile);
+        for (int ti = 0; ti < tiles; ++ti)
+          asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                       ::"r"(smem_u32(xring + slot * XSTAGE + ti * kTcXTile)), "l"(reinterpret_cast<uint64_t>(&amap)),
+                         "r"((kt0 + st * TPS + ti) * kBK), "r"(0), "r"(smem_u32(&afull[slot]))
+                       : "memory");
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    // instruction descriptor: D=f32, A=B=bf16, both K-major, N = NM, M = 128 (cute::UMMA::InstrDescriptor)
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcNM >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    // B smem descriptor (cute::UMMA::SmemDescriptor): K-major, SWIZZLE_128B, SBO = 1024 B (8-row groups), version 1
-    const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
-    for (int j = 0; j < nt; ++j) {
-      const int ab = j & 1, xs = j % kTcNSX;
-      mbar_wait(&afull[ab], (j >> 1) & 1);
-      mbar_wait(&xfull[xs], (j / kTcNSX) & 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t xaddr = smem_u32(xring + xs * kTcXTile);
+    // ===================== MMA issuer: a single thread =====================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N = NM, M = 128 (cute::UMMA::InstrDescriptor)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcNM >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      // B smem descriptor (cute::UMMA::SmemDescriptor): K-major, SWIZZLE_128B, SBO = 1024 B (8-row groups), version 1
+      const uint64_t desc_hi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
+      const uint32_t xbase = smem_u32(xring);
+      for (int st = 0; st < nst; ++st) {
+        const int ab = st % NAB, xs = st % kTcNSX;
+        mbar_wait(&afull[ab], (st / NAB) & 1);  // dequantized A stored in TMEM and activations landed
+        tc_fence_after();
+        TC_TRACE(1, st);
+        const int tiles = min(TPS, nt - st * TPS);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)((((xaddr + kk * 32) >> 4) & 0x3FFF) | (1u << 16));
-          if (WBITS == 4) {
-            tc_mma_ts(tmem + kTcColsD, tmem + kTcColsA + ab * ABUF + kk * 8, bdesc, idesc, (j > 0 || kk > 0) ? 1u : 0u);
-          } else {  // W8: per k16 step the buffer holds [lo plane | hi plane], 8 columns each
-            tc_mma_ts(tmem + kTcColsD, tmem + kTcColsA + ab * ABUF + kk * 16, bdesc, idesc, (j > 0 || kk > 0) ? 1u : 0u);
-            tc_mma_ts(tmem + kTcColsD, tmem + kTcColsA + ab * ABUF + kk * 16 + 8, bdesc, idesc, 1u);
+        for (int ti = 0; ti < TPS; ++ti) {
+          if (ti < tiles) {
+            const uint32_t xaddr = xbase + xs * XSTAGE + ti * kTcXTile;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t bdesc = desc_hi | (uint64_t)((((xaddr + kk * 32) >> 4) & 0x3FFF) | (1u << 16));
+              const uint32_t acc = (st > 0 || ti > 0 || kk > 0) ? 1u : 0u;
+              if (WBITS == 4) {
+                tc_mma_ts(tmem + kTcColsD, tmem + kTcColsA + ab * ABUF + ti * ACOLS + kk * 8, bdesc, idesc, acc);
+              } else {  // W8: per k16 step the buffer holds [lo plane | hi plane], 8 columns each
+                tc_mma_ts(tmem + kTcColsD, tmem + kTcColsA + ab * ABUF + kk * 16, bdesc, idesc, acc);
+                tc_mma_ts(tmem + kTcColsD, tmem + kTcColsA + ab * ABUF + kk * 16 + 8, bdesc, idesc, 1u);
+              }
+            }
           }
         }
-        tc_commit(&afree[ab]);
-        tc_commit(&xfree[xs]);
-        if (j == nt - 1) tc_commit(dfull);
+        tc_commit(&mdone[xs]);
+        if (st == nst - 1) tc_commit(dfull);
+        TC_TRACE(2, st);
       }
-      __syncwarp();
     }
   } else if (warp >= 6) {
-    // ===================== activation tiles + row sums =====================
-    const int xt = tid - 192;  // 0..63 == row m owned for the sums
-    pdl_wait();
-    float rsum = 0.f;
-    auto issue = [&](int jj) {
-      const int slot = jj % kTcNSX;
-      if (jj >= kTcNSX) mbar_wait(&xfree[slot], ((jj / kTcNSX) & 1) ^ 1);
-      uint8_t* dst = xring + slot * kTcXTile;
-      const int64_t k0 = (int64_t)(kt0 + jj) * kBK;
+    // ===================== row sums of the landed activation tiles (row = xt) =====================
+    const int xt = tid - 192;  // 0..63
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+    for (int st = 0; st < nst; ++st) {
+      const int slot = st % kTcNSX;
+      mbar_wait(&afull[slot], (st / kTcNSX) & 1);  // stage ready (implies its activation tiles landed)
+      const int tiles = min(TPS, nt - st * TPS);
+      for (int ti = 0; ti < tiles; ++ti) {
+        const uint32_t rbase = smem_u32(xring + slot * XSTAGE + ti * kTcXTile) + xt * 128;
 #pragma unroll
-      for (int i = 0; i < kTcNM * 8 / 64; ++i) {
-        const int idx = xt + i * 64;
-        const int row = idx >> 3, c = idx & 7;
-        const bool valid = row < p.M && (k0 + c * 8) < p.K;
-        const __nv_bfloat16* src = valid ? p.A + (int64_t)row * p.lda + k0 + c * 8 : p.A;
-        cp_async16_zfill(dst + row * 128 + ((c ^ (row & 7)) << 4), src, valid);
+        for (int c = 0; c < 8; c += 2) {
+          const uint4 v = lds128(rbase + ((c ^ (xt & 7)) << 4));
+          const uint4 w = lds128(rbase + (((c + 1) ^ (xt & 7)) << 4));
+          r0 += (bf16_lo(v.x) + bf16_hi(v.x)) + (bf16_lo(v.y) + bf16_hi(v.y));
+          r1 += (bf16_lo(v.z) + bf16_hi(v.z)) + (bf16_lo(v.w) + bf16_hi(v.w));
+          r2 += (bf16_lo(w.x) + bf16_hi(w.x)) + (bf16_lo(w.y) + bf16_hi(w.y));
+          r3 += (bf16_lo(w.z) + bf16_hi(w.z)) + (bf16_lo(w.w) + bf16_hi(w.w));
+        }
       }
-    };
-    for (int jj = 0; jj < kTcNSX - 1; ++jj) {
-      if (jj < nt) issue(jj);
-      cp_async_commit();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&xsum[slot]);
+      if (xt == 0) TC_TRACE(3, st);
     }
-    for (int j = 0; j < nt; ++j) {
-      if (j + kTcNSX - 1 < nt) issue(j + kTcNSX - 1);
-      cp_async_commit();
-      cp_async_wait<kTcNSX - 1>();
-      fence_proxy_async();               // generic-proxy writes -> visible to the tensor core (async proxy)
-      asm volatile("bar.sync 2, 64;" ::: "memory");
-      const int slot = j % kTcNSX;
-      if (xt == 0) mbar_arrive(&xfull[slot]);
-      // row sum of this tile (row = xt): 8 swizzled 16B chunks
-      const uint32_t rbase = smem_u32(xring + slot * kTcXTile) + xt * 128;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint4 v = lds128(rbase + ((c ^ (xt & 7)) << 4));
-        rsum += (bf16_lo(v.x) + bf16_hi(v.x)) + (bf16_lo(v.y) + bf16_hi(v.y)) + (bf16_lo(v.z) + bf16_hi(v.z)) +
-                (bf16_lo(v.w) + bf16_hi(v.w));
-      }
-      asm volatile("bar.sync 2, 64;" ::: "memory");  // all sums of this slot done before it can be refilled (issue waits xfree too)
-    }
-    suma[xt] = rsum;
+    suma[xt] = (r0 + r1) + (r2 + r3);
     asm volatile("bar.sync 3, 192;" ::: "memory");  // hand the sums to the epilogue warps
   } else {
     // ===================== dequant (warps 2..5) then epilogue =====================
     const int q = warp & 3;             // TMEM lane quadrant this warp may access
     const int r = q * 32 + lane;        // output channel (row of the 128-row tile)
-    const int n = ng * kBN + r;
-    const float2 sz = p.sz[n];          // per-channel (scale, zero + bias constant): immutable, read before the wait
+    const float2 sz = p.sz[ng * kBN + r];  // per-channel (scale, zero + bias constant): immutable, read before the wait
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     const uint32_t wring_u = smem_u32(wring);
     uint32_t woff[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) woff[c] = c * 2048 + ((r ^ tile_swz(WBITS, c)) << 4);
 
-    for (int j = 0; j < nt; ++j) {
-      const int slot = j % kTcNSW, ab = j & 1;
-      mbar_wait(&wfull[slot], (j / kTcNSW) & 1);
-      if (j >= 2) mbar_wait(&afree[ab], ((j >> 1) & 1) ^ 1);
+    for (int st = 0; st < nst; ++st) {
+      const int slot = st % kTcNSW, ab = st % NAB;
+      mbar_wait(&wfull[slot], (st / kTcNSW) & 1);
+      if (tid == 64) TC_TRACE(4, st);
+      if (st >= NAB) {  // A buffer ab was last read by stage st - NAB, whose commit went to mdone[(st - NAB) % NSX]
+        const int ps = st - NAB;
+        mbar_wait(&mdone[ps % kTcNSX], (ps / kTcNSX) & 1);
+      }
       tc_fence_after();
-      const uint32_t wt = wring_u + slot * TILE_BYTES;
-      if (WBITS == 4) {
+      if (tid == 64) TC_TRACE(5, st);
+      const int tiles = min(TPS, nt - st * TPS);
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const uint4 wv = lds128(wt + woff[c]);
-          const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+      for (int ti = 0; ti < TPS; ++ti) {
+        if (ti < tiles) {
+          const uint32_t wt = wring_u + slot * WSTAGE + ti * TILE_BYTES;
+          const uint32_t acol = trow + kTcColsA + ab * ABUF + ti * ACOLS;
+          if (WBITS == 4) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {  // k16 step kk = 2c + h: words 2h, 2h+1
-            uint32_t a[8];
+            for (int c = 0; c < 2; ++c) {
+              const uint4 wv = lds128(wt + woff[c]);
+              const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
-            for (int jw = 0; jw < 2; ++jw) {
-              const uint32_t w = ww[2 * h + jw];
-              a[4 * jw + 0] = lop3_and_or(w, kMask4, kMagic);
-              a[4 * jw + 1] = lop3_and_or(__funnelshift_r(w, w, 4), kMask4, kMagic);
-              a[4 * jw + 2] = lop3_and_or(__funnelshift_r(w, w, 8), kMask4, kMagic);
-              a[4 * jw + 3] = lop3_and_or(__funnelshift_r(w, w, 12), kMask4, kMagic);
+              for (int h = 0; h < 2; ++h) {  // k16 step kk = 2c + h: words 2h, 2h+1
+                uint32_t a[8];
+#pragma unroll
+                for (int jw = 0; jw < 2; ++jw) {
+                  const uint32_t w = ww[2 * h + jw];
+                  a[4 * jw + 0] = lop3_and_or(w, kMask4, kMagic);
+                  a[4 * jw + 1] = lop3_and_or(__funnelshift_r(w, w, 4), kMask4, kMagic);
+                  a[4 * jw + 2] = lop3_and_or(__funnelshift_r(w, w, 8), kMask4, kMagic);
+                  a[4 * jw + 3] = lop3_and_or(__funnelshift_r(w, w, 12), kMask4, kMagic);
+                }
+                tc_st8(acol + (2 * c + h) * 8, a);
+              }
             }
-            tc_st8(trow + kTcColsA + ab * ABUF + (2 * c + h) * 8, a);
-          }
-        }
-      } else {
+          } else {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {  // chunk c = k16 step kk
-          const uint4 wv = lds128(wt + woff[c]);
-          const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
-          uint32_t lo[8], hi[8];
+            for (int c = 0; c < 4; ++c) {  // chunk c = k16 step kk
+              const uint4 wv = lds128(wt + woff[c]);
+              const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+              uint32_t lo[8], hi[8];
 #pragma unroll
-          for (int jw = 0; jw < 4; ++jw) {
-            const uint32_t w = ww[jw];
-            lo[2 * jw + 0] = lop3_and_or(w, kMask4, kMagic);
-            hi[2 * jw + 0] = lop3_and_or(__funnelshift_r(w, w, 4), kMask4, kMagicHi);
-            lo[2 * jw + 1] = lop3_and_or(__funnelshift_r(w, w, 8), kMask4, kMagic);
-            hi[2 * jw + 1] = lop3_and_or(__funnelshift_r(w, w, 12), kMask4, kMagicHi);
+              for (int jw = 0; jw < 4; ++jw) {
+                const uint32_t w = ww[jw];
+                lo[2 * jw + 0] = lop3_and_or(w, kMask4, kMagic);
+                hi[2 * jw + 0] = lop3_and_or(__funnelshift_r(w, w, 4), kMask4, kMagicHi);
+                lo[2 * jw + 1] = lop3_and_or(__funnelshift_r(w, w, 8), kMask4, kMagic);
+                hi[2 * jw + 1] = lop3_and_or(__funnelshift_r(w, w, 12), kMask4, kMagicHi);
+              }
+              tc_st8(acol + c * 16, lo);
+              tc_st8(acol + c * 16 + 8, hi);
+            }
           }
-          tc_st8(trow + kTcColsA + ab * ABUF + c * 16, lo);
-          tc_st8(trow + kTcColsA + ab * ABUF + c * 16 + 8, hi);
         }
       }
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
+      if (tid == 64) TC_TRACE(6, st);
       if (lane == 0) {
         mbar_arrive(&wfree[slot]);
         mbar_arrive(&afull[ab]);
@@ -279,25 +325,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
     // ---------------- epilogue ----------------
     pdl_wait();  // workspace / counters / C belong to the previous kernels until here
     mbar_wait(dfull, 0);
+    if (tid == 64) TC_TRACE(7, 0);
     tc_fence_after();
     asm volatile("bar.sync 3, 192;" ::: "memory");  // row sums ready
     uint32_t d0[32], d1[32];
     tc_ld32(trow + kTcColsD, d0);
     tc_ld32(trow + kTcColsD + 32, d1);
     tc_wait_ld();
-    const int et = tid - 64;  // 0..127
-    const int MPK = kTcNM * kBN;
-    float v[kTcNM];
+    // park the dequantized tile in shared memory ([m][128 n] fp32, over the drained weight ring): the rest of the
+    // epilogue is a small rolled loop (a 64x unrolled register epilogue thrashes the instruction cache)
+    float* fs = reinterpret_cast<float*>(wring);
 #pragma unroll
     for (int m = 0; m < 32; ++m) {
-      v[m] = sz.x * (__uint_as_float(d0[m]) - sz.y * suma[m]);
-      v[m + 32] = sz.x * (__uint_as_float(d1[m]) - sz.y * suma[m + 32]);
+      fs[m * kBN + r] = sz.x * (__uint_as_float(d0[m]) - sz.y * suma[m]);
+      fs[(m + 32) * kBN + r] = sz.x * (__uint_as_float(d1[m]) - sz.y * suma[m + 32]);
     }
+    asm volatile("bar.sync 4, 128;" ::: "memory");
+    const int et = tid - 64;  // 0..127
+    const int MPK = kTcNM * kBN;
+    bool finalize = true;
     if (p.S > 1) {
       float* wsu = p.ws + ((size_t)ng * p.S + s) * MPK;
-#pragma unroll
-      for (int m = 0; m < kTcNM; ++m)
-        if (m < p.M) wsu[m * kBN + r] = v[m];
+      for (int i = et * 4; i < p.M * kBN; i += 128 * 4)
+        *reinterpret_cast<float4*>(wsu + i) = *reinterpret_cast<const float4*>(fs + i);
       __threadfence();
       asm volatile("bar.sync 4, 128;" ::: "memory");
       if (et == 0) {
@@ -305,51 +355,93 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
         s_is_last = (prev == (unsigned)(p.S - 1));
       }
       asm volatile("bar.sync 4, 128;" ::: "memory");
-      if (s_is_last) {
+      finalize = s_is_last != 0;
+      if (finalize) {
         __threadfence();
         const float* wsg = p.ws + (size_t)ng * p.S * MPK;
-#pragma unroll 4
-        for (int m = 0; m < kTcNM; ++m) {
-          if (m >= p.M) break;
-          float a = 0.f;
+        // fixed-order sum; 4 outputs x up to 8 partials = 32 independent 16-byte loads in flight per thread, so the
+        // whole reduction costs a handful of L2 round trips instead of one per output
+        const int lim = p.M * kBN;
+        for (int i0 = et * 4; i0 < lim; i0 += 128 * 4 * 4) {
+          float4 a[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) a[g] = make_float4(0.f, 0.f, 0.f, 0.f);
           for (int s0 = 0; s0 < p.S; s0 += 8) {
-            float b[8];
+            float4 b[4][8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) b[u] = (s0 + u < p.S) ? __ldcg(wsg + (size_t)(s0 + u) * MPK + m * kBN + r) : 0.f;
+            for (int g = 0; g < 4; ++g)
 #pragma unroll
-            for (int u = 0; u < 8; ++u) a += b[u];
+              for (int u = 0; u < 8; ++u) {
+                const int i = i0 + g * 512;
+                b[g][u] = (s0 + u < p.S && i < lim) ? __ldcg(reinterpret_cast<const float4*>(wsg + (size_t)(s0 + u) * MPK + i))
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+#pragma unroll
+              for (int u = 0; u < 8; ++u) { a[g].x += b[g][u].x; a[g].y += b[g][u].y; a[g].z += b[g][u].z; a[g].w += b[g][u].w; }
           }
-          v[m] = a;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int i = i0 + g * 512;
+            if (i < lim) *reinterpret_cast<float4*>(fs + i) = a[g];
+          }
         }
         if (et == 0) p.counters[ng] = 0;
+        asm volatile("bar.sync 4, 128;" ::: "memory");
       }
     }
-    if (p.S == 1 || s_is_last) {
-      if (n < p.N) {
-        const float bv = p.bias ? __bfloat162float(p.bias[n]) : 0.f;
-#pragma unroll
-        for (int m = 0; m < kTcNM; ++m) {
-          if (m < p.M) {
-            float o = apply_act_rt(v[m] * p.alpha + bv, p.act);
-            if (p.residual) o += __bfloat162float(p.residual[(int64_t)m * p.ldc + n]);
-            p.C[(int64_t)m * p.ldc + n] = __float2bfloat16(o);
-          }
+    if (tid == 64) TC_TRACE(7, 1);
+    if (finalize) {
+#pragma unroll 4
+      for (int i = et; i < p.M * (kBN / 2); i += 128) {
+        const int m = i >> 6, np = i & 63;
+        const int nn = ng * kBN + np * 2;
+        if (nn >= p.N) continue;
+        float v0 = fs[m * kBN + np * 2] * p.alpha, v1 = fs[m * kBN + np * 2 + 1] * p.alpha;
+        const bool has1 = (nn + 1) < p.N;
+        if (p.bias) {
+          v0 += __bfloat162float(p.bias[nn]);
+          if (has1) v1 += __bfloat162float(p.bias[nn + 1]);
+        }
+        v0 = apply_act_rt(v0, p.act);
+        v1 = apply_act_rt(v1, p.act);
+        __nv_bfloat16* cp = p.C + (int64_t)m * p.ldc + nn;
+        if (p.residual) {
+          const __nv_bfloat16* rp = p.residual + (int64_t)m * p.ldc + nn;
+          v0 += __bfloat162float(rp[0]);
+          if (has1) v1 += __bfloat162float(rp[1]);
+        }
+        if (has1 && ((reinterpret_cast<uintptr_t>(cp) & 3) == 0)) {
+          *reinterpret_cast<uint32_t*>(cp) = pack_bf16x2(v0, v1);
+        } else {
+          cp[0] = __float2bfloat16(v0);
+          if (has1) cp[1] = __float2bfloat16(v1);
         }
       }
     }
   }
 
+  if (tid == 64) TC_TRACE(7, 2);
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) TC_TRACE(7, 3);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTcTmemCols) : "memory");
   }
 }
 
+#ifdef B2_TC_TRACE
+extern "C" int b2_debug_tc_trace(unsigned long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_tc_trace, sizeof(g_tc_trace));
+}
+#endif
+
 int tc_smem_bytes(int wbits) {
-  const int tile = wbits == 4 ? 4096 : 8192;
-  return 1024 + kTcNSX * kTcXTile + kTcNSW * tile + kTcNM * 4 + 32 * 8 + 64;
+  const int tps = wbits == 4 ? 2 : 1;
+  const int wstage = tps * (wbits == 4 ? 4096 : 8192);
+  return 1024 + kTcNSX * tps * kTcXTile + kTcNSW * wstage + kTcNM * 4 + 40 * 8 + 64;
 }
 
 cudaError_t tc_configure(int wbits) {
@@ -357,13 +449,41 @@ cudaError_t tc_configure(int wbits) {
   return cudaFuncSetAttribute(wq_gemm_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(8));
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
 cudaError_t tc_launch(int wbits, const TcLaunch& a, cudaStream_t stream) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return cudaErrorNotSupported;
+  // activations A[M, K] bf16, row stride lda: box = 64 k x 64 rows, 128B swizzle, zero fill outside [M, K]
+  alignas(64) CUtensorMap amap;
+  const cuuint64_t gdim[2] = {(cuuint64_t)a.K, (cuuint64_t)a.M};
+  const cuuint64_t gstride[1] = {(cuuint64_t)a.lda * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kTcNM};
+  const cuuint32_t estr[2] = {1, 1};
+  if (enc(&amap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(a.A), gdim, gstride, box, estr,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return cudaErrorInvalidValue;
+
   TcParams p;
   p.packed = a.packed; p.sz = a.sz; p.A = a.A; p.lda = a.lda; p.C = a.C; p.ldc = a.ldc; p.bias = a.bias; p.residual = a.residual;
   p.ws = a.ws; p.counters = a.counters; p.M = a.M; p.N = a.N; p.K = a.K; p.Np = a.Np; p.KT = a.KT; p.NG = a.NG; p.S = a.S;
   p.act = a.act; p.alpha = a.alpha;
-  if (wbits == 4) return launch(wq_gemm_tc_kernel<4>, dim3(a.NG * a.S), dim3(kTcThreads), (size_t)tc_smem_bytes(4), stream, true, p);
-  return launch(wq_gemm_tc_kernel<8>, dim3(a.NG * a.S), dim3(kTcThreads), (size_t)tc_smem_bytes(8), stream, true, p);
+  if (wbits == 4) return launch(wq_gemm_tc_kernel<4>, dim3(a.NG * a.S), dim3(kTcThreads), (size_t)tc_smem_bytes(4), stream, true, p, amap);
+  return launch(wq_gemm_tc_kernel<8>, dim3(a.NG * a.S), dim3(kTcThreads), (size_t)tc_smem_bytes(8), stream, true, p, amap);
 }
 
 }  // namespace b2

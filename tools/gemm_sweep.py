@@ -64,8 +64,13 @@ if __name__ == "__main__":
                     print(f"{name:5s} M={M} env={env} pdl={pdl}: {us:7.2f} us  {gbs:7.1f} GB/s", flush=True)
     else:
         envs = [dict(kv.split("=") for kv in cfg.split(",") if kv) for cfg in sys.argv[2:]] or [{}]
-        for name, (K, N) in SHAPES.items():
-            for M in (1, 8):
+        ms = [int(x) for x in os.environ.get("SWEEP_M", "1,8").split(",")]
+        names = os.environ.get("SWEEP_SHAPES", "gate,down,qkv,o").split(",")
+        nw = int(os.environ.get("SWEEP_NW", "8"))
+        for name in names:
+            K, N = SHAPES[name]
+            for M in ms:
                 for env in envs:
-                    us, gbs = bench(K, N, M, env=env)
+                    e2 = dict(env); pdl = int(e2.pop('PDL', 1))
+                    us, gbs = bench(K, N, M, env=e2, nw=nw, pdl=pdl)
                     print(f"{name:5s} M={M} env={env}: {us:7.2f} us  {gbs:7.1f} GB/s", flush=True)
