@@ -1,0 +1,115 @@
+"""The allspark-shaped C++ operators (dash-infer_b200/host/) driven like the reference's TestOpUtil
+(tests/cpp/operator/cuda/operator_gemm_lowp_test.cpp:650-725): InitV2 -> Reshape -> Forward, checked against the oracle."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import kvcache_ref as KV
+from oracle import quant_ref as Q
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST_LIB = os.path.join(ROOT, "dash-infer_b200", "lib", "liballspark_b200.so")
+
+
+def _lib():
+    import b200spark  # noqa: F401  (loads libb200spark.so with RTLD_GLOBAL first)
+    lib = C.CDLL(HOST_LIB)
+    lib.as_test_gemm.restype = C.c_int
+    lib.as_test_gemm.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
+                                 C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.as_test_span_attn.restype = C.c_int
+    lib.as_test_span_attn.argtypes = [C.c_int] * 9 + [C.c_void_p, C.c_void_p]
+    lib.as_test_registered.restype = C.c_int
+    lib.as_test_registered.argtypes = [C.c_char_p]
+    return lib
+
+
+def test_host_library_loads_and_registers_ops():
+    """CPU-safe: the operator library loads and the factory knows the reference's op-type strings."""
+    lib = _lib()
+    for name in (b"GemmA16W4", b"GemmA16W8", b"Gemm", b"DecOptMHA", b"DecOptMQA"):
+        assert lib.as_test_registered(name) == 1, name
+    assert lib.as_test_registered(b"GemmA8W8") == 0  # out of scope: must not pretend
+
+
+def _bf16_np(t):
+    return t.contiguous().view(torch.int16).numpy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("op,group,M", [("GemmA16W4", -1, 1), ("GemmA16W4", -1, 17), ("GemmA16W4", 128, 5), ("GemmA16W8", -1, 3),
+                                        ("GemmA16W8", 128, 31), ("Gemm", -1, 8)])
+def test_gemm_operator_like_testoputil(op, group, M):
+    from b200spark import quantize as PQ
+    lib = _lib()
+    K, N = 1024, 640
+    g = torch.Generator().manual_seed(M + len(op))
+    w = (torch.randn(K, N, generator=g) * 0.02).to(torch.bfloat16)
+    a = (torch.rand(M, K, generator=g) * 2 - 1).to(torch.bfloat16)
+    bias = (torch.randn(N, generator=g) * 0.02).to(torch.bfloat16)
+    if op == "GemmA16W4":
+        q, s, z = PQ.quantize_a16w4(w, group); qu = Q.unpack_u4x2(q.numpy(), N); wdt = 10
+    elif op == "GemmA16W8":
+        q, s, z = PQ.quantize_a16w8(w, group); qu = q.numpy(); wdt = 3
+    else:
+        q, s, z = w, None, None; wdt = 9
+    out = np.zeros((M, N), np.int16)
+    qn = _bf16_np(q) if op == "Gemm" else q.contiguous().numpy()
+    an, bn = _bf16_np(a), _bf16_np(bias)
+    sn = _bf16_np(s) if s is not None else None
+    zn = _bf16_np(z) if z is not None else None
+    rc = lib.as_test_gemm(op.encode(), M, N, K, group, 5, 1.0, an.ctypes.data, qn.ctypes.data, wdt,
+                          sn.ctypes.data if sn is not None else None, zn.ctypes.data if zn is not None else None,
+                          bn.ctypes.data, out.ctypes.data)
+    assert rc == 0, rc
+    got = torch.from_numpy(out).view(torch.bfloat16).float().numpy()
+    if op == "Gemm":
+        ref = Q.activation((a.float().numpy().astype(np.float64) @ w.float().numpy().astype(np.float64)
+                            + bias.float().numpy()[None]).astype(np.float32), 5)
+    else:
+        ref = Q.gemm_wq_math(a.float().numpy(), qu, s.float().numpy(), z.float().numpy(), group, bias.float().numpy(), 5)
+    assert Q.err_min_abs_rel(ref, got) <= 2e-2
+
+
+@pytest.mark.gpu
+def test_gemm_operator_rejects_bad_configs():
+    lib = _lib()
+    K, N, M = 128, 64, 1
+    z16 = np.zeros((K, N), np.int16)
+    out = np.zeros((M, N), np.int16)
+    # GemmA16W4 with int8-typed packed weight: ALLSPARK_PARAM_ERROR (gemm_a16w4.cpp:104-110)
+    rc = lib.as_test_gemm(b"GemmA16W4", M, N, K, -1, 0, 1.0, z16.ctypes.data, z16.ctypes.data, 3, z16.ctypes.data, z16.ctypes.data,
+                          None, out.ctypes.data)
+    assert rc == 2
+    # GroupSize 24: rejected like gemm_a16w4.cpp:57-63
+    rc = lib.as_test_gemm(b"GemmA16W4", M, N, K, 24, 0, 1.0, z16.ctypes.data, z16.ctypes.data, 10, z16.ctypes.data, z16.ctypes.data,
+                          None, out.ctypes.data)
+    assert rc == 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("span,steps", [(16, 40), (128, 130)])
+def test_span_attention_operator_decode_loop(span, steps):
+    """DecOptMQA through Alloc/Forward for `steps` decode steps (spans claimed on demand), every step checked."""
+    lib = _lib()
+    B, nH, nG = 3, 8, 2
+    W, OW = (nH + 2 * nG) * 128, nH * 128
+    rng = np.random.default_rng(span)
+    qkv = torch.from_numpy(rng.standard_normal((steps, B, W)).astype(np.float32)).to(torch.bfloat16)
+    out = np.zeros((steps, B, OW), np.int16)
+    rc = lib.as_test_span_attn(B, steps, nH, nG, span, 0, 256, 3, 1, _bf16_np(qkv).ctypes.data, out.ctypes.data)
+    assert rc == 0, rc
+    got = torch.from_numpy(out).view(torch.bfloat16).float().numpy().reshape(steps, B, nH, 128)
+    kref, vref = KV.SpanCacheRef(KV.QUANT_NONE, span, nG), KV.SpanCacheRef(KV.QUANT_NONE, span, nG)
+    for _ in range(B):
+        kref.add_sequence(); vref.add_sequence()
+    x = qkv.float().numpy().reshape(steps, B, nH + 2 * nG, 128)
+    for t in range(steps):
+        for b in range(B):
+            kref.append(b, t, x[t, b, nH:nH + nG]); vref.append(b, t, x[t, b, nH + nG:])
+        if t in (0, 1, span - 1, span, steps - 1):
+            ref = KV.attention_ref(x[t, :, :nH], kref, vref, [t + 1] * B, nH, 1.0 / np.sqrt(128))
+            assert np.abs(got[t] - ref).max() <= 6e-3, t

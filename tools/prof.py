@@ -27,6 +27,10 @@ st = model.DecodeStack(model.QWEN2_7B, a.batch, a.ctx + 64, wbits=a.wbits, kv=a.
 if a.what in ("attn", "step"):
     st.set_context(a.ctx)
 torch.cuda.synchronize()
+if a.what == "step":
+    st.step()  # plans / workspace growth outside the profiled region
+    torch.cuda.synchronize()
+torch.cuda.profiler.start()
 for _ in range(a.iters):
     if a.what == "gemm":
         for L in st.layers:
@@ -41,4 +45,5 @@ for _ in range(a.iters):
     else:
         st.step()
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("done")
