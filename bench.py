@@ -200,8 +200,14 @@ def run_gpu(args):
                                                                          "frac": round(nb / t / 1e9 / hbm_peak, 3), "algo_bytes": nb,
                                                                          "note": "same weights every launch; 1.09 GB >> L2"}
         dom = "wq_gemm[gate %dx%d]" % (cfg.hidden, cfg.inter)
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            traffic = tj["wq_gemm_tc[gate] M=64"] if B > 16 else tj["wq_gemm[gate] M<=16"]
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["GBps"], "peak": hbm_peak, "unit": "GB/s",
-                "frac": kern[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": kern[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
                 "step": {"algo_bytes": step_bytes, "weights_bytes": wbytes, "kv_bytes": kvbytes,
                          "GBps": round(step_bytes / (ms * 1e-3 / K) / 1e9, 1),
                          "frac": round(step_bytes / (ms * 1e-3 / K) / 1e9 / hbm_peak, 3),
