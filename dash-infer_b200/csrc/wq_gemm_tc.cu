@@ -31,7 +31,7 @@ namespace b2 {
 
 constexpr int kTcThreads = 288;      // warp 0 weights TMA, 1 MMA, 2-5 dequant/epilogue, 6-7 row sums, 8 activation TMA
 constexpr int kTcNM = 64;            // batch columns per MMA (UMMA N)
-constexpr int kTcNSW = 4;            // weight stages (8 KB each)
+constexpr int kTcNSW = 12;           // weight stages (8 KB each): ~2 us of HBM latency x 44 GB/s/SM needs >= 80 KB in flight
 constexpr int kTcNSX = 3;            // {dequantized-A buffer in TMEM, activation slot in smem} stages
 constexpr int kTcXTile = kTcNM * 128;  // bytes: NM rows x 64 k bf16
 constexpr int kTcColsD = 0;          // TMEM columns [0, 64): accumulator
@@ -74,7 +74,7 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
 
 // optional timeline instrumentation (CTA 0 only): compiled in with -DB2_TC_TRACE
 #ifdef B2_TC_TRACE
-__device__ unsigned long long g_tc_trace[8][256];
+__device__ unsigned long long g_tc_trace[16][256];
 #define TC_TRACE(role, idx) do { if (blockIdx.x == 0 && (idx) < 256) g_tc_trace[role][idx] = clock64(); } while (0)
 #else
 #define TC_TRACE(role, idx) do {} while (0)
@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
             for (int kk = 0; kk < 4; ++kk) {
               const uint64_t bdesc = desc_hi | (uint64_t)((((xaddr + kk * 32) >> 4) & 0x3FFF) | (1u << 16));
               const uint32_t acc = (st > 0 || ti > 0 || kk > 0) ? 1u : 0u;
+              TC_TRACE(8 + ti * 4 + kk, st);
               if (WBITS == 4) {
                 tc_mma_ts(tmem + kTcColsD, tmem + kTcColsA + ab * ABUF + ti * ACOLS + kk * 8, bdesc, idesc, acc);
               } else {  // W8: per k16 step the buffer holds [lo plane | hi plane], 8 columns each

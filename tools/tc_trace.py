@@ -14,13 +14,13 @@ ws = ops.Workspace()
 for _ in range(3):
     out = h(a, ws)
 torch.cuda.synchronize()
-buf = (ctypes.c_ulonglong * (8 * 256))()
+buf = (ctypes.c_ulonglong * (16 * 256))()
 lib.b2_debug_tc_trace.argtypes = [ctypes.c_void_p]
 rc = lib.b2_debug_tc_trace(buf)
-t = [[buf[r * 256 + i] for i in range(256)] for r in range(8)]
+t = [[buf[r * 256 + i] for i in range(256)] for r in range(16)]
 t0 = t[7][4]
 names = ["prod_issue", "mma_ready", "mma_issued", "x_ready", "dq_wfull", "dq_afree", "dq_stored"]
 nt = max(i for i in range(256) if t[6][i]) + 1
 print("tiles", nt, "start", 0, "dfull", t[7][0] - t0, "pre-final", t[7][1] - t0, "epi_done", t[7][2] - t0, "end", t[7][3] - t0)
 for j in range(nt):
-    print(j, " ".join(f"{names[r]}={t[r][j] - t0:7d}" for r in range(7)))
+    print(j, " ".join(f"{names[r]}={t[r][j] - t0:7d}" for r in range(7)), "| mma issue deltas", [t[8 + i][j] - t[1][j] for i in range(8)])
