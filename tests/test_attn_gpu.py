@@ -100,3 +100,47 @@ def test_attention_none_long_and_ragged():
     ref = KV.attention_ref(q, kref, vref, lens, nH, 1.0 / np.sqrt(128))
     err = np.abs(out.float().cpu().numpy().reshape(B, nH, 128) - ref).max()
     assert err <= 6e-3, err
+
+
+def _close(got, ref):
+    # 2e-3 abs + bf16 rounding of the stored output / probabilities (2^-7 relative envelope)
+    return np.all(np.abs(got - ref) <= 2e-3 + 2.0 ** -7 * np.abs(ref)), float(np.abs(got - ref).max())
+
+
+@pytest.mark.parametrize("mode", [KV.QUANT_I8, KV.QUANT_U4])
+@pytest.mark.parametrize("span", [16, 128])
+@pytest.mark.parametrize("nH,nG", [(8, 2), (28, 4), (16, 1)])
+def test_attention_quantized_small(mode, span, nH, nG):
+    """I8 / U4 spans: attention against fp64 attention over the DEQUANTIZED oracle cache (same bytes, bit-exact append)."""
+    from b200spark import ops
+    lens = [1, 63, 64, 65, 200]
+    B = len(lens)
+    cache, kref, vref, q = _build(mode, B, lens, nH, nG, span, seed=span * 7 + nH + mode, max_len=256)
+    attn = ops.SpanAttn(cache.cfg, B)
+    ws = ops.Workspace()
+    new_lens = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    out = attn(_bf16(q.reshape(B, -1)).cuda(), cache, new_lens, 256, ws)
+    torch.cuda.synchronize()
+    ref = KV.attention_ref(q, kref, vref, lens, nH, 1.0 / np.sqrt(128))
+    ok, err = _close(out.float().cpu().numpy().reshape(B, nH, 128), ref)
+    assert ok, err
+
+
+@pytest.mark.parametrize("mode", [KV.QUANT_I8, KV.QUANT_U4])
+def test_attention_quantized_long(mode):
+    from b200spark import ops
+    nH, nG, span = 28, 4, 128
+    lens = [2048, 3000, 777]
+    B = len(lens)
+    cache, kref, vref, q = _build(mode, B, lens, nH, nG, span, seed=11 + mode, max_len=3072)
+    attn = ops.SpanAttn(cache.cfg, B)
+    ws = ops.Workspace()
+    new_lens = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    qd = _bf16(q.reshape(B, -1)).cuda()
+    out = attn(qd, cache, new_lens, 3072, ws)
+    out2 = attn(qd, cache, new_lens, 3072, ws)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+    ref = KV.attention_ref(q, kref, vref, lens, nH, 1.0 / np.sqrt(128))
+    ok, err = _close(out.float().cpu().numpy().reshape(B, nH, 128), ref)
+    assert ok, err

@@ -112,5 +112,7 @@ def test_span_attention_operator_decode_loop(span, steps):
             kref.append(b, t, x[t, b, nH:nH + nG]); vref.append(b, t, x[t, b, nH + nG:])
         if t in (0, 1, span - 1, span, steps - 1):
             ref = KV.attention_ref(x[t, :, :nH], kref, vref, [t + 1] * B, nH, 1.0 / np.sqrt(128))
-            # 2e-3 abs + bf16 rounding of the stored output and probabilities (2^-8 relative)
-            assert np.all(np.abs(got[t] - ref) <= 2e-3 + 2.0 ** -7 * np.abs(ref)), (t, np.abs(got[t] - ref).max())
+            # 2e-3 abs + bf16 rounding of the stored output (2^-7 |ref| envelope) and of the
+            # probabilities fed to the tensor core (2^-9 relative each, weighted by |V| <= vmax)
+            vmax = float(np.abs(x[:t + 1, :, nH + nG:]).max())
+            assert np.all(np.abs(got[t] - ref) <= 2e-3 + 2.0 ** -7 * np.abs(ref) + 2.0 ** -9 * vmax), (t, np.abs(got[t] - ref).max())

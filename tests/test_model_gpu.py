@@ -17,12 +17,12 @@ def _glue_refs():
     pass
 
 
-@pytest.mark.parametrize("wbits,group,kv", [(4, -1, "none"), (8, -1, "none"), (4, 128, "none")])
+@pytest.mark.parametrize("wbits,group,kv", [(4, -1, "none"), (8, -1, "none"), (4, 128, "none"), (8, -1, "i8"), (4, -1, "u4")])
 def test_tiny_decoder_logits_and_tokens(wbits, group, kv):
     from b200spark import model
     B, steps = 2, 6
     st = model.DecodeStack(model.TINY, B, 64, wbits=wbits, group=group, kv=kv, span=16, keep_ref=True)
-    ref = DR.from_stack(st, KV.QUANT_NONE)
+    ref = DR.from_stack(st, {"none": KV.QUANT_NONE, "i8": KV.QUANT_I8, "u4": KV.QUANT_U4}[kv])
     ref.reset(B)
     ids = torch.tensor([3, 777], dtype=torch.int64)
     for t in range(steps):
@@ -31,7 +31,9 @@ def test_tiny_decoder_logits_and_tokens(wbits, group, kv):
         torch.cuda.synchronize()
         glog = st.logits.float().cpu()
         rlog, rnext = ref.step(ids, [t] * B)
-        tol = 1e-2 * rlog.abs().max().item()
+        # u4 KV: a 1-ulp bf16 difference in a K/V row can move a 4-bit code by one step (1/15 of the row's range),
+        # so upstream rounding differences are amplified; the bound is widened for that mode only
+        tol = (4e-2 if kv == "u4" else 1e-2) * rlog.abs().max().item()
         err = (glog - rlog).abs().max().item()
         assert err <= tol, (t, err, tol)
         assert torch.equal(nxt, torch.argmax(glog, dim=-1)), "argmax kernel must be bit-exact on its own logits"
