@@ -107,13 +107,16 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    cfg = {"qwen2-7b": model.QWEN2_7B, "llama3-8b": model.LLAMA3_8B, "tiny": model.TINY}[args.model]
+    cfg = {"qwen2-7b": model.QWEN2_7B, "llama3-8b": model.LLAMA3_8B, "qwen2-72b": model.QWEN2_72B, "tiny": model.TINY}[args.model]
     B, ctx, K, W = args.batch, args.ctx, args.steps, max(args.warmup, 3)
+    tp = args.tp
+    if tp > 1 and tp != world:
+        raise SystemExit("--tp N must equal the torchrun world size (one rank per GPU)")
     hbm_peak, peak_src = peaks()
     max_len = ctx + W + K + 2 * K + 16
     t_build = time.time()
     st = model.DecodeStack(cfg, B, max_len, wbits=args.wbits, group=args.group, kv=args.kv, span=args.span,
-                           layers=args.layers)
+                           layers=args.layers, tp_rank=rank if tp > 1 else 0, tp_size=tp)
     st.set_context(ctx)
     st.capture()
     t_build = time.time() - t_build
@@ -146,7 +149,8 @@ def run_gpu(args):
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    value = world * B * K / (ms * 1e-3)
+    replicas = 1 if tp > 1 else world  # TP: the ranks share one batch; replicas: every rank has its own
+    value = replicas * B * K / (ms * 1e-3)
 
     # ---------------- e2e: host buffers through the public API, H2D of ids + D2H of the sampled ids every step
     ids_host = ids.pin_memory()
@@ -166,7 +170,7 @@ def run_gpu(args):
         t = torch.tensor([e2e_s], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_val = world * B * K / e2e_s
+    e2e_val = replicas * B * K / e2e_s
 
     out = None
     if rank == 0:
@@ -213,6 +217,9 @@ def run_gpu(args):
                          "frac": round(step_bytes / (ms * 1e-3 / K) / 1e9 / hbm_peak, 3),
                          "roofline_tok_s": round(B / (step_bytes / (hbm_peak * 1e9)), 1)}}
         cpu = None
+        if tp > 1:
+            # per-rank bytes: weights/tp (+ replicated params), KV/tp; the roofline is per GPU
+            roof["step"]["note"] = "per-rank algorithmic bytes; tokens/s is for the whole TP group"
         if world == 1 and not args.no_cpu:
             from oracle import decoder_ref as DR
             r = DR.time_cpu_decode(cfg, B, ctx, sample_layers=2, steps=2, warmup=1)
@@ -221,13 +228,14 @@ def run_gpu(args):
                              "fp32 contiguous KV at ctx %d, batch %d; per-layer time x %d layers + head" % (cfg.layers, ctx, B, cfg.layers)}
         out = {
             "metric": METRIC, "value": round(value, 2), "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "strong" if tp > 1 else "weak", "vs_baseline": None,
             "dtype": "bf16 activations x int%d weights (fp32 accumulate), %s KV" % (args.wbits, args.kv),
             "data": "synthetic (seeded N(0,0.02^2) weights quantized with the IQ formula; N(0,1) KV rows written by the append kernel)",
             "config": {"workload": "%s IQ-int%d%s weight-only decode, batch %d, ctx %d, 1xB200 per replica" %
                                    (cfg.name, args.wbits, "" if args.group == -1 else " g%d" % args.group, B, ctx),
                        "batch": B, "ctx": ctx, "layers": len(st.layers), "kv_cache": args.kv, "span": args.span,
-                       "parallelism": "replicas x%d (no data-path collective)" % world,
+                       "parallelism": ("tp%d (column/row split, NCCL all-reduce after o_proj and down_proj, vocab-split lm_head)" % tp)
+                                      if tp > 1 else "replicas x%d (no data-path collective)" % world,
                        "l2": "inputs larger than L2: %.2f GB streamed per step vs 126 MB L2" % (step_bytes / 1e9),
                        "cuda_graph": True, "pdl": os.environ.get("B2_PDL", "1") != "0"},
             "e2e": {"value": round(e2e_val, 2), "unit": "tokens/s", "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": B * 8},
@@ -288,6 +296,7 @@ def main():
     ap.add_argument("--span", type=int, default=128)
     ap.add_argument("--layers", type=int, default=None, help="debug: fewer layers (INVALID as a bench number)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--tp", type=int, default=1, help="tensor-parallel degree: all ranks of the torchrun job form ONE model instance")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

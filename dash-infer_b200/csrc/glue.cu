@@ -109,8 +109,8 @@ __global__ void __launch_bounds__(128) embedding_kernel(__nv_bfloat16* __restric
 }
 
 // greedy sampling: lowest index among the maxima (bit-exact index contract)
-__global__ void __launch_bounds__(1024) argmax_kernel(int64_t* __restrict__ ids_out, const __nv_bfloat16* __restrict__ logits, int n,
-                                                      int64_t ld) {
+__global__ void __launch_bounds__(1024) argmax_kernel(int64_t* __restrict__ ids_out, float* __restrict__ vals_out,
+                                                      const __nv_bfloat16* __restrict__ logits, int n, int64_t ld, int64_t id_offset) {
   pdl_wait();
   pdl_launch_dependents();
   __shared__ float sv[32];
@@ -140,7 +140,10 @@ __global__ void __launch_bounds__(1024) argmax_kernel(int64_t* __restrict__ ids_
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
       if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
     }
-    if (threadIdx.x == 0) ids_out[b] = bi;
+    if (threadIdx.x == 0) {
+      ids_out[b] = bi + id_offset;
+      if (vals_out) vals_out[b] = best;
+    }
   }
 }
 
@@ -203,8 +206,16 @@ int b2_embedding(void* out, const void* table, const int64_t* ids, int batch, in
 
 int b2_argmax(int64_t* ids_out, const void* logits, int batch, int n, int64_t ld, void* stream) {
   if (!ids_out || !logits || batch <= 0 || n <= 0) return B2_ERR_PARAM;
-  B2_LAUNCH_CHECK("argmax", launch(argmax_kernel, dim3(batch), dim3(1024), 0, (cudaStream_t)stream, true, ids_out,
-                                   (const __nv_bfloat16*)logits, n, ld));
+  B2_LAUNCH_CHECK("argmax", launch(argmax_kernel, dim3(batch), dim3(1024), 0, (cudaStream_t)stream, true, ids_out, (float*)nullptr,
+                                   (const __nv_bfloat16*)logits, n, ld, (int64_t)0));
+  return B2_OK;
+}
+
+int b2_argmax_shard(int64_t* ids_out, float* vals_out, const void* logits, int batch, int n, int64_t ld, int64_t id_offset,
+                    void* stream) {
+  if (!ids_out || !vals_out || !logits || batch <= 0 || n <= 0) return B2_ERR_PARAM;
+  B2_LAUNCH_CHECK("argmax_shard", launch(argmax_kernel, dim3(batch), dim3(1024), 0, (cudaStream_t)stream, true, ids_out, vals_out,
+                                         (const __nv_bfloat16*)logits, n, ld, id_offset));
   return B2_OK;
 }
 

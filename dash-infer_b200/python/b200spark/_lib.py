@@ -14,7 +14,7 @@ SYMBOLS = [
     "b2_gemm_wq_attach_packed", "b2_gemm_wq_workspace_bytes", "b2_gemm_wq_run", "b2_gemm_wq_algo_bytes",
     "b2_span_bytes", "b2_span_cache_append", "b2_span_attn_create", "b2_span_attn_destroy",
     "b2_span_attn_workspace_bytes", "b2_span_attn_run", "b2_span_attn_algo_bytes",
-    "b2_rmsnorm", "b2_rotary", "b2_binary", "b2_embedding", "b2_argmax", "b2_lens_add",
+    "b2_rmsnorm", "b2_rotary", "b2_binary", "b2_embedding", "b2_argmax", "b2_argmax_shard", "b2_lens_add",
 ]
 
 
@@ -75,6 +75,7 @@ def _load():
         "b2_binary": (i32, [vp, vp, vp, i64, i32, vp]),
         "b2_embedding": (i32, [vp, vp, vp, i32, i32, vp]),
         "b2_argmax": (i32, [vp, vp, i32, i32, i64, vp]),
+        "b2_argmax_shard": (i32, [vp, vp, vp, i32, i32, i64, i64, vp]),
         "b2_lens_add": (i32, [vp, i32, i32, vp]),
     }
     for name, (res, args) in sig.items():

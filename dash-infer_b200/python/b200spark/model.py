@@ -14,7 +14,7 @@ from dataclasses import dataclass
 
 import torch
 
-from . import ops, quantize as PQ
+from . import ops, quantize as PQ, tp as TP
 from ._lib import ACT_NONE, ACT_SILU, BIN_MUL, KV_I8, KV_NONE, KV_U4
 
 
@@ -46,24 +46,34 @@ def synth_weight(K, N, gen, device, std=0.02):
 
 
 class QuantLinear:
-    """One projection: synthetic bf16 weight -> IQ quantizer -> GemmWQ handle (keeps nothing but the handle)."""
+    """One projection: synthetic bf16 weight -> IQ quantizer -> (TP shard) -> GemmWQ handle (keeps nothing but the handle).
+    shard: None | ("cols", ranges) | ("rows", rank, tp)."""
 
-    def __init__(self, K, N, wbits, group, gen, device, max_m, bias=False, keep_ref=False):
+    def __init__(self, K, N, wbits, group, gen, device, max_m, bias=False, keep_ref=False, shard=None):
         w = synth_weight(K, N, gen, device)
         b = (torch.randn(N, generator=gen, device=device) * 0.02).to(torch.bfloat16) if bias else None
-        self.K, self.N, self.wbits = K, N, wbits
-        self.op = ops.GemmWQ(K, N, wbits, group, max_m=max_m)
         if wbits == 4:
             q, s, z = PQ.quantize_a16w4(w, group)
         elif wbits == 8:
             q, s, z = PQ.quantize_a16w8(w, group)
         else:
             q, s, z = w, None, None
-        self.op.prepare(q, s, z, b)
         self.ref = None
-        if keep_ref:  # dense fp32 (q - z) * s for the CPU oracle
+        if keep_ref:  # dense fp32 (q - z) * s of the FULL matrix for the CPU oracle
             self.ref = (PQ.dequantize(q, s, z, group, wbits, N) if wbits != 16 else w.float()).cpu()
             self.ref_bias = b.float().cpu() if b is not None else None
+        if shard is not None:
+            if shard[0] == "cols":
+                q, s, z, b = TP.shard_cols(q, s, z, b, wbits, shard[1])
+                N = sum(e - a for a, e in shard[1])
+            else:
+                q, s, z = TP.shard_rows(q, s, z, wbits, group, shard[1], shard[2])
+                K = q.shape[0]
+                if shard[1] != 0:
+                    b = None  # a row-split bias is added once (rank 0)
+        self.K, self.N, self.wbits = K, N, wbits
+        self.op = ops.GemmWQ(K, N, wbits, group, max_m=max_m)
+        self.op.prepare(q.contiguous(), s, z, b)
 
     def __call__(self, x, ws, **kw):
         return self.op(x, ws, **kw)
@@ -71,28 +81,41 @@ class QuantLinear:
 
 class DecodeStack:
     def __init__(self, cfg, batch, max_len, wbits=4, group=-1, kv="none", span=128, seed=1234, device="cuda",
-                 keep_ref=False, layers=None):
+                 keep_ref=False, layers=None, tp_rank=0, tp_size=1, tp_group=None):
+        """tp_size > 1: the reference's tensor-parallel layout (QKV/gate/up column split, o/down row split + all-reduce,
+        vocab-split lm_head + B-element all-gather); every rank builds the SAME full synthetic weights from `seed` and
+        keeps its shard, exactly like the reference splits an already-quantized checkpoint."""
         self.cfg, self.B, self.max_len = cfg, batch, max_len
+        self.tp_rank, self.tp, self.tp_group = tp_rank, tp_size, tp_group
         self.device = device
         self.n_layers = layers if layers is not None else cfg.layers
         self.kv_mode = KV_MODES[kv]
         gen = torch.Generator(device=device).manual_seed(seed)
         H, nH, nG, I = cfg.hidden, cfg.n_heads, cfg.n_kv, cfg.inter
+        tp, r = tp_size, tp_rank
+        self.nH_l, self.nG_l, self.I_l = nH // tp, nG // tp, I // tp
+        nHl, nGl = self.nH_l, self.nG_l
+        col_qkv = ("cols", TP.col_ranges_qkv(nH, nG, r, tp)) if tp > 1 else None
+        col_i = ("cols", TP.col_range_even(I, r, tp)) if tp > 1 else None
+        row = ("rows", r, tp) if tp > 1 else None
         self.embed = synth_weight(cfg.vocab, H, gen, device, std=1.0)
         self.layers = []
         for _ in range(self.n_layers):
             L = {}
             L["g1"] = (1.0 + 0.1 * torch.randn(H, generator=gen, device=device)).to(torch.bfloat16)
-            L["qkv"] = QuantLinear(H, (nH + 2 * nG) * 128, wbits, group, gen, device, batch, bias=cfg.qkv_bias, keep_ref=keep_ref)
-            L["o"] = QuantLinear(nH * 128, H, wbits, group, gen, device, batch, keep_ref=keep_ref)
+            L["qkv"] = QuantLinear(H, (nH + 2 * nG) * 128, wbits, group, gen, device, batch, bias=cfg.qkv_bias, keep_ref=keep_ref,
+                                   shard=col_qkv)
+            L["o"] = QuantLinear(nH * 128, H, wbits, group, gen, device, batch, keep_ref=keep_ref, shard=row)
             L["g2"] = (1.0 + 0.1 * torch.randn(H, generator=gen, device=device)).to(torch.bfloat16)
-            L["gate"] = QuantLinear(H, I, wbits, group, gen, device, batch, keep_ref=keep_ref)
-            L["up"] = QuantLinear(H, I, wbits, group, gen, device, batch, keep_ref=keep_ref)
-            L["down"] = QuantLinear(I, H, wbits, group, gen, device, batch, keep_ref=keep_ref)
-            L["cache"] = ops.SpanCache(batch, max_len, nH, nG, span, self.kv_mode, device)
+            L["gate"] = QuantLinear(H, I, wbits, group, gen, device, batch, keep_ref=keep_ref, shard=col_i)
+            L["up"] = QuantLinear(H, I, wbits, group, gen, device, batch, keep_ref=keep_ref, shard=col_i)
+            L["down"] = QuantLinear(I, H, wbits, group, gen, device, batch, keep_ref=keep_ref, shard=row)
+            L["cache"] = ops.SpanCache(batch, max_len, nHl, nGl, span, self.kv_mode, device)
             self.layers.append(L)
         self.gf = (1.0 + 0.1 * torch.randn(H, generator=gen, device=device)).to(torch.bfloat16)
-        self.lm_head = QuantLinear(H, cfg.vocab, 16, -1, gen, device, batch, keep_ref=keep_ref)
+        self.vocab_l = cfg.vocab // tp
+        self.lm_head = QuantLinear(H, cfg.vocab, 16, -1, gen, device, batch, keep_ref=keep_ref,
+                                   shard=("cols", TP.col_range_even(cfg.vocab, r, tp)) if tp > 1 else None)
         self.attn = ops.SpanAttn(self.layers[0]["cache"].cfg, batch)
         self.ws = ops.Workspace(device)
         self.rope = (cfg.rope_base, 128)
@@ -104,12 +127,18 @@ class DecodeStack:
         bf = dict(dtype=torch.bfloat16, device=device)
         self.x = torch.empty(batch, H, **bf)
         self.xn = torch.empty(batch, H, **bf)
-        self.qkv = torch.empty(batch, (nH + 2 * nG) * 128, **bf)
-        self.q = torch.empty(batch, nH * 128, **bf)
-        self.ao = torch.empty(batch, nH * 128, **bf)
-        self.gate = torch.empty(batch, I, **bf)
-        self.up = torch.empty(batch, I, **bf)
-        self.logits = torch.empty(batch, cfg.vocab, **bf)
+        self.qkv = torch.empty(batch, (nHl + 2 * nGl) * 128, **bf)
+        self.q = torch.empty(batch, nHl * 128, **bf)
+        self.ao = torch.empty(batch, nHl * 128, **bf)
+        self.gate = torch.empty(batch, self.I_l, **bf)
+        self.up = torch.empty(batch, self.I_l, **bf)
+        self.logits = torch.empty(batch, self.vocab_l, **bf)
+        if tp > 1:
+            self.part = torch.empty(batch, H, **bf)                       # row-split partial sums (all-reduced)
+            self.loc_ids = torch.empty(batch, dtype=torch.int64, device=device)
+            self.loc_val = torch.empty(batch, dtype=torch.float32, device=device)
+            self.all_ids = torch.empty(tp, batch, dtype=torch.int64, device=device)
+            self.all_val = torch.empty(tp, batch, dtype=torch.float32, device=device)
         self.graph = None
         self.launches_per_step = 0
 
@@ -119,7 +148,7 @@ class DecodeStack:
         realistic params), and set the sequence lengths."""
         cfg = self.cfg
         gen = torch.Generator(device=self.device).manual_seed(seed)
-        width = (cfg.n_heads + 2 * cfg.n_kv) * 128
+        width = (self.nH_l + 2 * self.nG_l) * 128
         pos = torch.zeros(self.B, dtype=torch.int32, device=self.device)
         for t in range(ctx):
             rows = torch.randn(self.B, width, generator=gen, device=self.device).to(torch.bfloat16)
@@ -131,6 +160,19 @@ class DecodeStack:
         torch.cuda.synchronize()
 
     # ------------------------------------------------------------------ one decode step (eager or captured)
+    def _row_parallel(self, lin, inp, n):
+        """o_proj / down_proj.  TP=1: residual fused in the GEMM epilogue.  TP>1: partial sums (rank 0 carries the
+        residual), all-reduce over NVLink (reference: AllReduceOp after o_proj and down_proj, allreduce_op.cpp:73-115 —
+        here stream-ordered, no host sync)."""
+        import torch.distributed as dist
+        if self.tp == 1:
+            lin(inp, self.ws, out=self.x, residual=self.x)
+            return n + 1
+        lin(inp, self.ws, out=self.part, residual=self.x if self.tp_rank == 0 else None)
+        dist.all_reduce(self.part, group=self.tp_group)
+        self.x.copy_(self.part)
+        return n + 1
+
     def _step_ops(self):
         cfg, ws = self.cfg, self.ws
         n = 0
@@ -140,18 +182,26 @@ class DecodeStack:
             L["qkv"](self.xn, ws, out=self.qkv); n += 1
             ops.cache_append(L["cache"], self.qkv, self.lens_old, q_out=self.q, rope=self.rope); n += 1
             self.attn(self.q, L["cache"], self.lens_new, self.max_len, ws, out=self.ao); n += 1
-            L["o"](self.ao, ws, out=self.x, residual=self.x); n += 1
+            n = self._row_parallel(L["o"], self.ao, n)
             ops.rmsnorm(self.x, L["g2"], cfg.eps, out=self.xn); n += 1
             L["gate"](self.xn, ws, out=self.gate, act=ACT_SILU); n += 1
             L["up"](self.xn, ws, out=self.up); n += 1
             ops.binary(self.gate, self.up, BIN_MUL, out=self.gate); n += 1
-            L["down"](self.gate, ws, out=self.x, residual=self.x); n += 1
+            n = self._row_parallel(L["down"], self.gate, n)
         ops.rmsnorm(self.x, self.gf, cfg.eps, out=self.xn); n += 1
         self.lm_head(self.xn, ws, out=self.logits); n += 1
-        ops.argmax(self.logits, out=self.next_ids); n += 1
+        if self.tp == 1:
+            ops.argmax(self.logits, out=self.next_ids); n += 1
+        else:  # vocab-split lm_head: local (max, argmax) + B-element all-gather instead of all-reducing 152064 logits
+            import torch.distributed as dist
+            ops.argmax_shard(self.logits, self.tp_rank * self.vocab_l, self.loc_ids, self.loc_val); n += 1
+            dist.all_gather_into_tensor(self.all_val, self.loc_val, group=self.tp_group)
+            dist.all_gather_into_tensor(self.all_ids, self.loc_ids, group=self.tp_group)
+            win = torch.argmax(self.all_val, dim=0)  # lowest rank on ties == lowest vocab index
+            self.next_ids.copy_(torch.gather(self.all_ids, 0, win[None, :])[0])
         ops.lens_add(self.lens_old, 1); n += 1
         ops.lens_add(self.lens_new, 1); n += 1
-        mchunks = (self.B + 31) // 32  # the small-M GEMM runs M > 32 in row chunks of 32
+        mchunks = (self.B + 63) // 64 if self.B > 16 else 1  # rows per launch: 64 (tcgen05 path) / all (small-M path)
         n += (mchunks - 1) * (5 * len(self.layers) + 1)
         self.launches_per_step = n
 

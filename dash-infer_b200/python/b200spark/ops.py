@@ -191,6 +191,13 @@ def argmax(logits, out=None):
     return out
 
 
+def argmax_shard(logits, id_offset, ids_out, vals_out):
+    B, n = logits.shape
+    check(lib.b2_argmax_shard(_ptr(ids_out), _ptr(vals_out), _ptr(logits), B, n, logits.stride(0), int(id_offset), _stream()),
+          "b2_argmax_shard")
+    return ids_out, vals_out
+
+
 def lens_add(lens, delta):
     check(lib.b2_lens_add(_ptr(lens), lens.numel(), int(delta), _stream()), "b2_lens_add")
     return lens

@@ -171,6 +171,10 @@ int b2_binary(void* out, const void* a, const void* b, int64_t n, int op, void* 
 int b2_embedding(void* out, const void* table, const int64_t* ids, int batch, int hidden, void* stream);
 /* ids_out[b] = argmax_n logits[b,n] (lowest index on ties); logits FT [batch, ld] */
 int b2_argmax(int64_t* ids_out, const void* logits, int batch, int n, int64_t ld, void* stream);
+/* vocab-sharded lm_head (tensor parallel): per-rank argmax of its shard, ids offset by the shard start, plus the max
+ * value (fp32) so the ranks can pick the global winner with a B-element all-gather instead of all-reducing logits. */
+int b2_argmax_shard(int64_t* ids_out, float* vals_out, const void* logits, int batch, int n, int64_t ld,
+                    int64_t id_offset, void* stream);
 /* lens[b] += delta for b < batch (keeps sequence lengths device-resident under CUDA graphs) */
 int b2_lens_add(int32_t* lens, int batch, int delta, void* stream);
 

@@ -1,0 +1,68 @@
+"""2-GPU tensor-parallel parity (skipped unless two CUDA devices are visible): a TP=2 decode stack over NCCL must produce
+the same tokens / logits (within bf16 partial-sum rounding) as the single-GPU stack built from the same seed."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "dash-infer_b200", "python"))
+    import torch.distributed as dist
+    from b200spark import model
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    B, steps = 3, 5
+    st = model.DecodeStack(model.TINY, B, 64, wbits=4, span=16, seed=7, tp_rank=rank, tp_size=world)
+    one = model.DecodeStack(model.TINY, B, 64, wbits=4, span=16, seed=7)
+    ids = torch.tensor([1, 2, 3], dtype=torch.int64, device="cuda")
+    ok, worst = True, 0.0
+    for t in range(steps):
+        st.ids.copy_(ids); one.ids.copy_(ids)
+        n_tp = st.step().clone(); n_one = one.step().clone()
+        torch.cuda.synchronize()
+        full = one.logits.float()
+        loc = st.logits.float()
+        ref = full[:, rank * st.vocab_l:(rank + 1) * st.vocab_l]
+        worst = max(worst, ((loc - ref).abs().max() / full.abs().max()).item())
+        top2 = torch.topk(full, 2, dim=-1).values
+        for b in range(B):
+            if (top2[b, 0] - top2[b, 1]).item() > 0.04 * full.abs().max().item():
+                ok = ok and (n_tp[b].item() == n_one[b].item())
+        ids = n_one
+    ret[rank] = (ok, worst)
+    dist.destroy_process_group()
+
+
+def test_tp2_matches_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    for r in range(2):
+        ok, worst = ret[r]
+        assert worst < 2e-2, worst
+        assert ok
