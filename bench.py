@@ -179,7 +179,8 @@ def run_gpu(args):
         xn = st.xn
         rounds = max(2, 112 // max(1, len(st.layers)))
         kern = {}
-        io = {"gate": (xn, st.gate), "up": (xn, st.up), "qkv": (xn, st.qkv), "o": (st.ao, st.x), "down": (st.gate, st.x)}
+        io = {"gate": (xn, st.gate), "gateup": (xn, st.gate), "up": (xn, st.up), "qkv": (xn, st.qkv), "o": (st.ao, st.x),
+              "down": (st.gate, st.x)}
 
         def gemm_entry(name, key, act=0):
             src, dst = io[key]
@@ -188,7 +189,9 @@ def run_gpu(args):
             nb = st.layers[0][key].op.algo_bytes(B)
             kern[name] = {"us": round(t * 1e6, 2), "GBps": round(nb / t / 1e9, 1), "frac": round(nb / t / 1e9 / hbm_peak, 3),
                           "algo_bytes": nb}
-        gemm_entry("wq_gemm[gate %dx%d]" % (cfg.hidden, cfg.inter), "gate", ACT_SILU)
+        fused = st.fuse_swiglu
+        dom = "wq_gemm[gate+up SwiGLU %dx2x%d]" % (cfg.hidden, cfg.inter) if fused else "wq_gemm[gate %dx%d]" % (cfg.hidden, cfg.inter)
+        gemm_entry(dom, "gateup" if fused else "gate", 0 if fused else ACT_SILU)
         gemm_entry("wq_gemm[down %dx%d]" % (cfg.inter, cfg.hidden), "down")
         gemm_entry("wq_gemm[qkv %dx%d]" % (cfg.hidden, (cfg.n_heads + 2 * cfg.n_kv) * 128), "qkv")
         gemm_entry("wq_gemm[o %dx%d]" % (cfg.n_heads * 128, cfg.hidden), "o")
@@ -203,11 +206,12 @@ def run_gpu(args):
         kern["wq_gemm[lm_head bf16 %dx%d]" % (cfg.hidden, cfg.vocab)] = {"us": round(t * 1e6, 2), "GBps": round(nb / t / 1e9, 1),
                                                                          "frac": round(nb / t / 1e9 / hbm_peak, 3), "algo_bytes": nb,
                                                                          "note": "same weights every launch; 1.09 GB >> L2"}
-        dom = "wq_gemm[gate %dx%d]" % (cfg.hidden, cfg.inter)
         traffic = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-            traffic = tj["wq_gemm_tc[gate] M=64"] if B > 16 else tj["wq_gemm[gate] M<=16"]
+            key = ("wq_gemm_tc[gate+up] M=64" if B > 16 else "wq_gemm[gate+up] M<=16") if fused else \
+                  ("wq_gemm_tc[gate] M=64" if B > 16 else "wq_gemm[gate] M<=16")
+            traffic = tj.get(key)
         except Exception:
             pass
         roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["GBps"], "peak": hbm_peak, "unit": "GB/s",
@@ -248,8 +252,14 @@ def run_gpu(args):
         }
         print(json.dumps(out), flush=True)
     if world > 1:
+        # rank 0 spent extra time in the per-kernel section: let everybody meet, then leave WITHOUT tearing the
+        # communicator down (destroying a process group whose collectives were captured in live CUDA graphs hung on
+        # the 2-GPU box); a hard exit after the barrier is clean for torchrun (exit code 0 on every rank)
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
     return out
 
 

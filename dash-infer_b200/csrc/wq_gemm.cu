@@ -325,6 +325,23 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
   }
 
   // ---- final: alpha, bias, activation, residual, bf16 store (coalesced along n)
+  if (p.act == B2_ACT_SWIGLU) {  // tile = [64 gate | 64 up] channels of n in [64*ng, 64*ng+64): out = silu(gate) * up
+    for (int i = ctid; i < p.M * 32; i += kWarps * 32) {
+      const int m = i >> 5, np = i & 31;
+      const int n = ng * 64 + np * 2;
+      if (n >= p.N) continue;
+      const float g0 = fs[m * kBN + np * 2] * p.alpha, g1 = fs[m * kBN + np * 2 + 1] * p.alpha;
+      const float u0 = fs[m * kBN + 64 + np * 2] * p.alpha, u1 = fs[m * kBN + 64 + np * 2 + 1] * p.alpha;
+      const float v0 = apply_act<B2_ACT_SILU>(g0) * u0, v1 = apply_act<B2_ACT_SILU>(g1) * u1;
+      __nv_bfloat16* cp = p.C + (int64_t)m * p.ldc + n;
+      if ((n + 1) < p.N && ((reinterpret_cast<uintptr_t>(cp) & 3) == 0)) *reinterpret_cast<uint32_t*>(cp) = pack_bf16x2(v0, v1);
+      else {
+        cp[0] = __float2bfloat16(v0);
+        if ((n + 1) < p.N) cp[1] = __float2bfloat16(v1);
+      }
+    }
+    return;
+  }
   for (int i = ctid; i < p.M * (kBN / 2); i += kWarps * 32) {
     const int m = i >> 6, np = i & 63;
     const int n = ng * kBN + np * 2;
@@ -356,7 +373,9 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
 // init-time re-layout kernels (reference layouts -> tile image).  One thread per 32-bit word.
 // ------------------------------------------------------------------------------------------------
 // One thread per 32-bit word of the image: word index -> (tile, chunk, stored row, word j) -> logical row/k.
-__global__ void pack_w4_kernel(uint32_t* __restrict__ dst, const uint8_t* __restrict__ q, int K, int N, int KT, int NG) {
+// pair != 0: rows 0..63 of every 128-row tile come from q (gate), rows 64..127 from q2 (up), both [K, N]
+__global__ void pack_w4_kernel(uint32_t* __restrict__ dst, const uint8_t* __restrict__ q, const uint8_t* __restrict__ q2, int pair,
+                               int K, int N, int KT, int NG) {
   const int64_t total = (int64_t)NG * KT * 1024;
   const int npack = (N + 1) / 2;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -366,13 +385,14 @@ __global__ void pack_w4_kernel(uint32_t* __restrict__ dst, const uint8_t* __rest
     const int64_t tile = i >> 10;
     const int kt = tile % KT, ng = tile / KT;
     const int r = rs ^ tile_swz(4, c);
-    const int n = ng * kBN + r;
+    const int n = pair ? ng * 64 + (r & 63) : ng * kBN + r;
+    const uint8_t* qs = (pair && r >= 64) ? q2 : q;
     uint32_t word = 0;
     for (int nb = 0; nb < 8; ++nb) {
       const int k = kt * kBK + 32 * c + 8 * j + 2 * (nb & 3) + (nb >> 2);
       uint32_t v = 0;
       if (n < N && k < K) {
-        const uint8_t b = q[(int64_t)k * npack + (n >> 1)];
+        const uint8_t b = qs[(int64_t)k * npack + (n >> 1)];
         v = (n & 1) ? (b >> 4) : (b & 0xF);
       }
       word |= v << (4 * nb);
@@ -381,8 +401,8 @@ __global__ void pack_w4_kernel(uint32_t* __restrict__ dst, const uint8_t* __rest
   }
 }
 
-__global__ void pack_w8_kernel(uint32_t* __restrict__ dst, const uint8_t* __restrict__ q, int K, int N, int KT, int NG,
-                               int is_signed) {
+__global__ void pack_w8_kernel(uint32_t* __restrict__ dst, const uint8_t* __restrict__ q, const uint8_t* __restrict__ q2, int pair,
+                               int K, int N, int KT, int NG, int is_signed) {
   const int64_t total = (int64_t)NG * KT * 2048;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int j = i & 3;
@@ -391,20 +411,22 @@ __global__ void pack_w8_kernel(uint32_t* __restrict__ dst, const uint8_t* __rest
     const int64_t tile = i >> 11;
     const int kt = tile % KT, ng = tile / KT;
     const int r = rs ^ tile_swz(8, c);
-    const int n = ng * kBN + r;
+    const int n = pair ? ng * 64 + (r & 63) : ng * kBN + r;
+    const uint8_t* qs = (pair && r >= 64) ? q2 : q;
     uint32_t word = 0;
     for (int b = 0; b < 4; ++b) {
       const int kk = (b == 0) ? 0 : (b == 2 ? 1 : (b == 1 ? 2 : 3));  // bytes (b0,b2,b1,b3) hold k+0,1,2,3
       const int k = kt * kBK + 16 * c + 4 * j + kk;
       uint32_t v = is_signed ? 0x80u : 0u;
-      if (n < N && k < K) v = q[(int64_t)k * N + n] ^ (is_signed ? 0x80u : 0u);
+      if (n < N && k < K) v = qs[(int64_t)k * N + n] ^ (is_signed ? 0x80u : 0u);
       word |= v << (8 * b);
     }
     dst[i] = (word << 3) | (word >> 29);
   }
 }
 
-__global__ void pack_w16_kernel(uint32_t* __restrict__ dst, const uint16_t* __restrict__ wsrc, int K, int N, int KT, int NG) {
+__global__ void pack_w16_kernel(uint32_t* __restrict__ dst, const uint16_t* __restrict__ wsrc, const uint16_t* __restrict__ wsrc2,
+                                int pair, int K, int N, int KT, int NG) {
   const int64_t total = (int64_t)NG * KT * 4096;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int j = i & 3;
@@ -413,12 +435,13 @@ __global__ void pack_w16_kernel(uint32_t* __restrict__ dst, const uint16_t* __re
     const int64_t tile = i >> 12;
     const int kt = tile % KT, ng = tile / KT;
     const int r = rs ^ tile_swz(16, c);
-    const int n = ng * kBN + r;
+    const int n = pair ? ng * 64 + (r & 63) : ng * kBN + r;
+    const uint16_t* ws = (pair && r >= 64) ? wsrc2 : wsrc;
     uint32_t word = 0;
     for (int e = 0; e < 2; ++e) {
       const int k = kt * kBK + 8 * c + 2 * j + e;
       uint32_t v = 0;
-      if (n < N && k < K) v = wsrc[(int64_t)k * N + n];
+      if (n < N && k < K) v = ws[(int64_t)k * N + n];
       word |= v << (16 * e);
     }
     dst[i] = word;
@@ -427,12 +450,17 @@ __global__ void pack_w16_kernel(uint32_t* __restrict__ dst, const uint16_t* __re
 
 // (scale, zero) bf16 [G][N] -> float2 [G][Np] with the integer-bias constant folded into the zero
 __global__ void pack_sz_kernel(float2* __restrict__ dst, const __nv_bfloat16* __restrict__ scales,
-                               const __nv_bfloat16* __restrict__ zeros, int G, int N, int Np, float zbias) {
+                               const __nv_bfloat16* __restrict__ zeros, const __nv_bfloat16* __restrict__ scales2,
+                               const __nv_bfloat16* __restrict__ zeros2, int pair, int G, int N, int Np, float zbias) {
   const int64_t total = (int64_t)G * Np;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int n = i % Np, gi = i / Np;
+    const int np = i % Np, gi = i / Np;
+    const int r = np & (kBN - 1), ng = np / kBN;
+    const int n = pair ? ng * 64 + (r & 63) : np;
+    const __nv_bfloat16* sc = (pair && r >= 64) ? scales2 : scales;
+    const __nv_bfloat16* zr = (pair && r >= 64) ? zeros2 : zeros;
     float2 v = make_float2(0.f, 0.f);
-    if (n < N) v = make_float2(__bfloat162float(scales[(int64_t)gi * N + n]), __bfloat162float(zeros[(int64_t)gi * N + n]) + zbias);
+    if (n < N) v = make_float2(__bfloat162float(sc[(int64_t)gi * N + n]), __bfloat162float(zr[(int64_t)gi * N + n]) + zbias);
     dst[i] = v;
   }
 }
@@ -460,6 +488,7 @@ struct b2_gemm_wq {
   unsigned* counters = nullptr;
   Plan plans[3];  // MT = 1, 2, 4
   int tc_S = 0;   // split-K of the tcgen05 path (0 = not planned)
+  bool pair = false;  // gate/up pair image (SwiGLU epilogue): physical channels = 2 * N
   int device = 0;
 };
 
@@ -558,7 +587,8 @@ int b2_gemm_wq_create(b2_gemm_wq_t* out, const b2_gemm_wq_desc* d) {
   const bool grouped = d->wbits != 16 && d->group_size != -1;
   const int kq = grouped ? d->group_size : kBK;
   h->Kp = (d->K + kq - 1) / kq * kq;
-  h->Np = (d->N + kBN - 1) / kBN * kBN;
+  h->pair = d->reserved == 1;
+  h->Np = h->pair ? (d->N + 63) / 64 * kBN : (d->N + kBN - 1) / kBN * kBN;  // pair: 64 gate + 64 up channels per tile
   h->KT = h->Kp / kBK;
   h->NG = h->Np / kBN;
   h->group_tiles = grouped ? d->group_size / kBK : 0;
@@ -588,12 +618,14 @@ int b2_gemm_wq_destroy(b2_gemm_wq_t h) {
 
 size_t b2_gemm_wq_packed_bytes(b2_gemm_wq_t h) { return h ? h->packed_bytes : 0; }
 
-int b2_gemm_wq_prepare_weights(b2_gemm_wq_t h, const void* qdata, const void* scales, const void* zeros,
-                               void* packed_dst, void* stream_) {
+static int prepare_impl(b2_gemm_wq_t h, const void* qdata, const void* scales, const void* zeros, const void* qdata2,
+                        const void* scales2, const void* zeros2, void* packed_dst, void* stream_) {
   if (!h || !qdata) return B2_ERR_PARAM;
   cudaStream_t stream = (cudaStream_t)stream_;
   const b2_gemm_wq_desc& d = h->d;
-  if (d.wbits != 16 && (!scales || !zeros)) return B2_ERR_PARAM;
+  const int pair = h->pair ? 1 : 0;
+  if (pair && !qdata2) return B2_ERR_PARAM;
+  if (d.wbits != 16 && (!scales || !zeros || (pair && (!scales2 || !zeros2)))) return B2_ERR_PARAM;
   if (packed_dst) {
     if (h->own_packed && h->packed) cudaFree(h->packed);
     h->packed = packed_dst;
@@ -606,12 +638,14 @@ int b2_gemm_wq_prepare_weights(b2_gemm_wq_t h, const void* qdata, const void* sc
   const int64_t words = (int64_t)h->packed_bytes / 4;
   const int blocks = (int)((words + threads - 1) / threads > 65535 * 8 ? 65535 * 8 : (words + threads - 1) / threads);
   if (d.wbits == 4)
-    pack_w4_kernel<<<blocks, threads, 0, stream>>>((uint32_t*)h->packed, (const uint8_t*)qdata, d.K, d.N, h->KT, h->NG);
+    pack_w4_kernel<<<blocks, threads, 0, stream>>>((uint32_t*)h->packed, (const uint8_t*)qdata, (const uint8_t*)qdata2, pair, d.K, d.N,
+                                                   h->KT, h->NG);
   else if (d.wbits == 8)
-    pack_w8_kernel<<<blocks, threads, 0, stream>>>((uint32_t*)h->packed, (const uint8_t*)qdata, d.K, d.N, h->KT, h->NG,
-                                                   d.qtype == B2_DT_I8);
+    pack_w8_kernel<<<blocks, threads, 0, stream>>>((uint32_t*)h->packed, (const uint8_t*)qdata, (const uint8_t*)qdata2, pair, d.K, d.N,
+                                                   h->KT, h->NG, d.qtype == B2_DT_I8);
   else
-    pack_w16_kernel<<<blocks, threads, 0, stream>>>((uint32_t*)h->packed, (const uint16_t*)qdata, d.K, d.N, h->KT, h->NG);
+    pack_w16_kernel<<<blocks, threads, 0, stream>>>((uint32_t*)h->packed, (const uint16_t*)qdata, (const uint16_t*)qdata2, pair, d.K,
+                                                    d.N, h->KT, h->NG);
   if (int st = launch_failed("pack_weights")) return st;
   if (d.wbits != 16) {
     if (!h->sz || !h->own_sz) {
@@ -620,13 +654,25 @@ int b2_gemm_wq_prepare_weights(b2_gemm_wq_t h, const void* qdata, const void* sc
     }
     // 16+q trick: W4 raw = sum a*(16+q); W8 raw = 16*sum a*(16+hi) + sum a*(16+lo) = sum a*(272+u), u = q (+128 if int8)
     const float zbias = d.wbits == 4 ? 16.f : (d.qtype == B2_DT_I8 ? 272.f + 128.f : 272.f);
-    // scales/zeros given for ceil(K/group) groups; groups beyond that (K padding) never occur since Kp/group == ceil
     const int64_t tot = (int64_t)h->G * h->Np;
-    pack_sz_kernel<<<(int)((tot + 255) / 256), 256, 0, stream>>>(h->sz, (const __nv_bfloat16*)scales,
-                                                                 (const __nv_bfloat16*)zeros, h->G, d.N, h->Np, zbias);
+    pack_sz_kernel<<<(int)((tot + 255) / 256), 256, 0, stream>>>(h->sz, (const __nv_bfloat16*)scales, (const __nv_bfloat16*)zeros,
+                                                                 (const __nv_bfloat16*)scales2, (const __nv_bfloat16*)zeros2, pair,
+                                                                 h->G, d.N, h->Np, zbias);
     if (int st = launch_failed("pack_sz")) return st;
   }
   return B2_OK;
+}
+
+int b2_gemm_wq_prepare_weights(b2_gemm_wq_t h, const void* qdata, const void* scales, const void* zeros,
+                               void* packed_dst, void* stream_) {
+  if (h && h->pair) return B2_ERR_PARAM;  // a paired handle takes two weight sets (b2_gemm_wq_prepare_swiglu)
+  return prepare_impl(h, qdata, scales, zeros, nullptr, nullptr, nullptr, packed_dst, stream_);
+}
+
+int b2_gemm_wq_prepare_swiglu(b2_gemm_wq_t h, const void* q_gate, const void* s_gate, const void* z_gate, const void* q_up,
+                              const void* s_up, const void* z_up, void* stream_) {
+  if (!h || !h->pair) return B2_ERR_PARAM;
+  return prepare_impl(h, q_gate, s_gate, z_gate, q_up, s_up, z_up, nullptr, stream_);
 }
 
 int b2_gemm_wq_attach_packed(b2_gemm_wq_t h, const void* packed, const void* scales_f32, const void* zeros_f32) {
@@ -681,8 +727,9 @@ size_t b2_gemm_wq_workspace_bytes(b2_gemm_wq_t h, int M) {
 size_t b2_gemm_wq_algo_bytes(b2_gemm_wq_t h, int M) {
   if (!h) return 0;
   const b2_gemm_wq_desc& d = h->d;
-  size_t w = (size_t)d.K * d.N * d.wbits / 8;
-  size_t prm = d.wbits == 16 ? 0 : (size_t)2 * 2 * h->G * d.N;
+  const size_t mul = h->pair ? 2 : 1;
+  size_t w = mul * (size_t)d.K * d.N * d.wbits / 8;
+  size_t prm = d.wbits == 16 ? 0 : mul * (size_t)2 * 2 * h->G * d.N;
   return w + prm + (size_t)2 * M * ((size_t)d.K + d.N);
 }
 
@@ -692,7 +739,9 @@ int b2_gemm_wq_run(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, int64_t 
   if (!h || !A || !C || M <= 0) return B2_ERR_PARAM;
   if (!h->packed) return B2_ERR_RUNTIME;
   if (M > h->d.max_m) return B2_ERR_LIMIT;
-  if (activation < 0 || activation > B2_ACT_SIGMOID) return B2_ERR_PARAM;
+  if (h->pair != (activation == B2_ACT_SWIGLU)) return B2_ERR_PARAM;  // paired image <=> SwiGLU epilogue
+  if (activation != B2_ACT_SWIGLU && (activation < 0 || activation > B2_ACT_SIGMOID)) return B2_ERR_PARAM;
+  if (h->pair && (bias || residual)) return B2_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (lda % 8) != 0) return B2_ERR_UNSUPPORTED;
   if (workspace_bytes < b2_gemm_wq_workspace_bytes(h, M)) return B2_ERR_PARAM;
   cudaStream_t stream = (cudaStream_t)stream_;

@@ -393,7 +393,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
       }
     }
     if (tid == 64) TC_TRACE(7, 1);
-    if (finalize) {
+    if (finalize && p.act == B2_ACT_SWIGLU) {  // tile = [64 gate | 64 up]: out[m, 64*ng + c] = silu(gate) * up
+      for (int i = et; i < p.M * 32; i += 128) {
+        const int m = i >> 5, np = i & 31;
+        const int nn = ng * 64 + np * 2;
+        if (nn >= p.N) continue;
+        const float g0 = fs[m * kBN + np * 2] * p.alpha, g1 = fs[m * kBN + np * 2 + 1] * p.alpha;
+        const float u0 = fs[m * kBN + 64 + np * 2] * p.alpha, u1 = fs[m * kBN + 64 + np * 2 + 1] * p.alpha;
+        const float v0 = apply_act<B2_ACT_SILU>(g0) * u0, v1 = apply_act<B2_ACT_SILU>(g1) * u1;
+        __nv_bfloat16* cp = p.C + (int64_t)m * p.ldc + nn;
+        if ((nn + 1) < p.N && ((reinterpret_cast<uintptr_t>(cp) & 3) == 0)) *reinterpret_cast<uint32_t*>(cp) = pack_bf16x2(v0, v1);
+        else {
+          cp[0] = __float2bfloat16(v0);
+          if ((nn + 1) < p.N) cp[1] = __float2bfloat16(v1);
+        }
+      }
+    } else if (finalize) {
 #pragma unroll 4
       for (int i = et; i < p.M * (kBN / 2); i += 128) {
         const int m = i >> 6, np = i & 63;

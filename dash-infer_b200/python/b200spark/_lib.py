@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(LIB_DIR, "libb200spark.so")
 SYMBOLS = [
     "b2_status_string", "b2_last_error", "b2_version", "b2_set_pdl",
     "b2_gemm_wq_create", "b2_gemm_wq_destroy", "b2_gemm_wq_packed_bytes", "b2_gemm_wq_prepare_weights",
-    "b2_gemm_wq_attach_packed", "b2_gemm_wq_workspace_bytes", "b2_gemm_wq_run", "b2_gemm_wq_algo_bytes",
+    "b2_gemm_wq_prepare_swiglu", "b2_gemm_wq_attach_packed", "b2_gemm_wq_workspace_bytes", "b2_gemm_wq_run", "b2_gemm_wq_algo_bytes",
     "b2_span_bytes", "b2_span_cache_append", "b2_span_attn_create", "b2_span_attn_destroy",
     "b2_span_attn_workspace_bytes", "b2_span_attn_run", "b2_span_attn_algo_bytes",
     "b2_rmsnorm", "b2_rotary", "b2_binary", "b2_embedding", "b2_argmax", "b2_argmax_shard", "b2_lens_add",
@@ -35,6 +35,7 @@ class RopeCfg(C.Structure):
 
 DT_F32, DT_F16, DT_I8, DT_BF16, DT_U8 = 1, 2, 3, 9, 10
 ACT_NONE, ACT_TANH, ACT_GELU_ERF, ACT_GELU_TANH, ACT_RELU, ACT_SILU, ACT_SIGMOID = range(7)
+ACT_SWIGLU = 100
 BIN_ADD, BIN_MUL = 1, 2
 KV_NONE, KV_I8, KV_U4 = 0, 1, 2
 
@@ -59,6 +60,7 @@ def _load():
         "b2_gemm_wq_destroy": (i32, [vp]),
         "b2_gemm_wq_packed_bytes": (sz, [vp]),
         "b2_gemm_wq_prepare_weights": (i32, [vp, vp, vp, vp, vp, vp]),
+        "b2_gemm_wq_prepare_swiglu": (i32, [vp, vp, vp, vp, vp, vp, vp, vp]),
         "b2_gemm_wq_attach_packed": (i32, [vp, vp, vp, vp]),
         "b2_gemm_wq_workspace_bytes": (sz, [vp, i32]),
         "b2_gemm_wq_run": (i32, [vp, vp, i64, vp, i64, i32, vp, vp, i32, f32, vp, sz, vp]),

@@ -79,14 +79,52 @@ class QuantLinear:
         return self.op(x, ws, **kw)
 
 
+class SwiGLULinear:
+    """gate_proj + up_proj as ONE weight stream with a fused silu(gate)*up epilogue (b2_gemm_wq_prepare_swiglu).
+    Weights are drawn in the same order as two separate QuantLinear's (gate first) so both graphs see identical values."""
+
+    def __init__(self, K, N, wbits, group, gen, device, max_m, keep_ref=False, shard=None):
+        qs = []
+        self.ref = []
+        for _ in range(2):
+            w = synth_weight(K, N, gen, device)
+            if wbits == 4:
+                q, s, z = PQ.quantize_a16w4(w, group)
+            elif wbits == 8:
+                q, s, z = PQ.quantize_a16w8(w, group)
+            else:
+                q, s, z = w, None, None
+            if keep_ref:
+                self.ref.append((PQ.dequantize(q, s, z, group, wbits, N) if wbits != 16 else w.float()).cpu())
+            if shard is not None:
+                q, s, z, _ = TP.shard_cols(q, s, z, None, wbits, shard[1])
+            qs.append((q, s, z))
+        if shard is not None:
+            N = sum(e - a for a, e in shard[1])
+        self.K, self.N = K, N
+        self.op = ops.GemmWQ(K, N, wbits, group, max_m=max_m, pair=True)
+        self.op.prepare_swiglu(*qs[0], *qs[1])
+
+    def __call__(self, x, ws, **kw):
+        return self.op(x, ws, **kw)
+
+
+class _RefView:
+    """Makes a SwiGLULinear look like the separate gate / up projections to the CPU oracle (decoder_ref.from_stack)."""
+
+    def __init__(self, ref):
+        self.ref, self.ref_bias = ref, None
+
+
 class DecodeStack:
     def __init__(self, cfg, batch, max_len, wbits=4, group=-1, kv="none", span=128, seed=1234, device="cuda",
-                 keep_ref=False, layers=None, tp_rank=0, tp_size=1, tp_group=None):
+                 keep_ref=False, layers=None, tp_rank=0, tp_size=1, tp_group=None, fuse_swiglu=True):
         """tp_size > 1: the reference's tensor-parallel layout (QKV/gate/up column split, o/down row split + all-reduce,
         vocab-split lm_head + B-element all-gather); every rank builds the SAME full synthetic weights from `seed` and
         keeps its shard, exactly like the reference splits an already-quantized checkpoint."""
         self.cfg, self.B, self.max_len = cfg, batch, max_len
         self.tp_rank, self.tp, self.tp_group = tp_rank, tp_size, tp_group
+        self.fuse_swiglu = fuse_swiglu
         self.device = device
         self.n_layers = layers if layers is not None else cfg.layers
         self.kv_mode = KV_MODES[kv]
@@ -107,8 +145,13 @@ class DecodeStack:
                                    shard=col_qkv)
             L["o"] = QuantLinear(nH * 128, H, wbits, group, gen, device, batch, keep_ref=keep_ref, shard=row)
             L["g2"] = (1.0 + 0.1 * torch.randn(H, generator=gen, device=device)).to(torch.bfloat16)
-            L["gate"] = QuantLinear(H, I, wbits, group, gen, device, batch, keep_ref=keep_ref, shard=col_i)
-            L["up"] = QuantLinear(H, I, wbits, group, gen, device, batch, keep_ref=keep_ref, shard=col_i)
+            if fuse_swiglu:
+                L["gateup"] = SwiGLULinear(H, I, wbits, group, gen, device, batch, keep_ref=keep_ref, shard=col_i)
+                if keep_ref:
+                    L["gate"], L["up"] = _RefView(L["gateup"].ref[0]), _RefView(L["gateup"].ref[1])
+            else:
+                L["gate"] = QuantLinear(H, I, wbits, group, gen, device, batch, keep_ref=keep_ref, shard=col_i)
+                L["up"] = QuantLinear(H, I, wbits, group, gen, device, batch, keep_ref=keep_ref, shard=col_i)
             L["down"] = QuantLinear(I, H, wbits, group, gen, device, batch, keep_ref=keep_ref, shard=row)
             L["cache"] = ops.SpanCache(batch, max_len, nHl, nGl, span, self.kv_mode, device)
             self.layers.append(L)
@@ -184,9 +227,12 @@ class DecodeStack:
             self.attn(self.q, L["cache"], self.lens_new, self.max_len, ws, out=self.ao); n += 1
             n = self._row_parallel(L["o"], self.ao, n)
             ops.rmsnorm(self.x, L["g2"], cfg.eps, out=self.xn); n += 1
-            L["gate"](self.xn, ws, out=self.gate, act=ACT_SILU); n += 1
-            L["up"](self.xn, ws, out=self.up); n += 1
-            ops.binary(self.gate, self.up, BIN_MUL, out=self.gate); n += 1
+            if self.fuse_swiglu:
+                L["gateup"](self.xn, ws, out=self.gate); n += 1
+            else:
+                L["gate"](self.xn, ws, out=self.gate, act=ACT_SILU); n += 1
+                L["up"](self.xn, ws, out=self.up); n += 1
+                ops.binary(self.gate, self.up, BIN_MUL, out=self.gate); n += 1
             n = self._row_parallel(L["down"], self.gate, n)
         ops.rmsnorm(self.x, self.gf, cfg.eps, out=self.xn); n += 1
         self.lm_head(self.xn, ws, out=self.logits); n += 1
@@ -202,7 +248,7 @@ class DecodeStack:
         ops.lens_add(self.lens_old, 1); n += 1
         ops.lens_add(self.lens_new, 1); n += 1
         mchunks = (self.B + 63) // 64 if self.B > 16 else 1  # rows per launch: 64 (tcgen05 path) / all (small-M path)
-        n += (mchunks - 1) * (5 * len(self.layers) + 1)
+        n += (mchunks - 1) * ((4 if self.fuse_swiglu else 5) * len(self.layers) + 1)
         self.launches_per_step = n
 
     def step(self):
@@ -231,7 +277,7 @@ class DecodeStack:
         """quantized projection weights + params + bf16 lm_head + KV of every sequence."""
         wbytes = 0
         for L in self.layers:
-            for k in ("qkv", "o", "gate", "up", "down"):
+            for k in (("qkv", "o", "gateup", "down") if self.fuse_swiglu else ("qkv", "o", "gate", "up", "down")):
                 wbytes += L[k].op.algo_bytes(0)
         wbytes += self.lm_head.op.algo_bytes(0)
         kv = self.attn.algo_bytes(self.B * (ctx + 1)) * len(self.layers)

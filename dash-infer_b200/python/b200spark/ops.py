@@ -36,11 +36,12 @@ class Workspace:
 class GemmWQ:
     """GemmA16W4 / GemmA16W8 / dense Gemm (wbits 16) handle."""
 
-    def __init__(self, K, N, wbits, group_size=-1, max_m=64, signed=True):
-        self.K, self.N, self.wbits, self.group_size, self.max_m = K, N, wbits, group_size, max_m
+    def __init__(self, K, N, wbits, group_size=-1, max_m=64, signed=True, pair=False):
+        """pair=True: gate/up weight pair with a fused SwiGLU epilogue (N = intermediate size)."""
+        self.K, self.N, self.wbits, self.group_size, self.max_m, self.pair = K, N, wbits, group_size, max_m, pair
         self.h = C.c_void_p()
         qtype = DT_U8 if wbits == 4 or not signed else DT_I8
-        d = GemmDesc(K, N, wbits, group_size if wbits != 16 else -1, DT_BF16, qtype, max_m, 0)
+        d = GemmDesc(K, N, wbits, group_size if wbits != 16 else -1, DT_BF16, qtype, max_m, 1 if pair else 0)
         check(lib.b2_gemm_wq_create(C.byref(self.h), C.byref(d)), "b2_gemm_wq_create")
         self.bias = None
 
@@ -55,6 +56,15 @@ class GemmWQ:
         torch.cuda.current_stream().synchronize()  # the caller may free qdata right after
         return self
 
+    def prepare_swiglu(self, qg, sg, zg, qu, su, zu):
+        assert self.pair
+        c = lambda t: t.contiguous() if t is not None else None
+        qg, sg, zg, qu, su, zu = map(c, (qg, sg, zg, qu, su, zu))
+        check(lib.b2_gemm_wq_prepare_swiglu(self.h, _ptr(qg), _ptr(sg), _ptr(zg), _ptr(qu), _ptr(su), _ptr(zu), _stream()),
+              "b2_gemm_wq_prepare_swiglu")
+        torch.cuda.current_stream().synchronize()
+        return self
+
     def workspace_bytes(self, M):
         return lib.b2_gemm_wq_workspace_bytes(self.h, M)
 
@@ -65,6 +75,8 @@ class GemmWQ:
         return lib.b2_gemm_wq_packed_bytes(self.h)
 
     def __call__(self, a, ws, out=None, act=ACT_NONE, alpha=1.0, residual=None):
+        if self.pair:
+            act = _lib.ACT_SWIGLU
         M = a.numel() // a.shape[-1]
         assert a.dtype == torch.bfloat16 and a.shape[-1] == self.K and a.stride(-1) == 1
         if out is None:

@@ -56,6 +56,8 @@ enum { B2_DT_F32 = 1, B2_DT_F16 = 2, B2_DT_I8 = 3, B2_DT_BF16 = 9, B2_DT_U8 = 10
 enum { B2_ACT_NONE = 0, B2_ACT_TANH = 1, B2_ACT_GELU_ERF = 2, B2_ACT_GELU_TANH = 3, B2_ACT_RELU = 4,
        B2_ACT_SILU = 5, B2_ACT_SIGMOID = 6 };
 enum { B2_BIN_ADD = 1, B2_BIN_MUL = 2 };
+/* extension (not a reference UnaryType): fused SwiGLU epilogue of a gate/up weight pair, see b2_gemm_wq_prepare_swiglu */
+enum { B2_ACT_SWIGLU = 100 };
 /* span::QuantMode (span_attn.h:41-48) */
 enum { B2_KV_NONE = 0, B2_KV_I8 = 1, B2_KV_U4 = 2 };
 
@@ -90,6 +92,12 @@ size_t b2_gemm_wq_packed_bytes(b2_gemm_wq_t handle);
  * instead of handle-owned memory — this is how two op instances share one image. */
 int b2_gemm_wq_prepare_weights(b2_gemm_wq_t handle, const void* qdata, const void* scales,
                                const void* zeros, void* packed_dst, void* stream);
+/* Fusion of the reference's three ops  GemmA16Wx(gate, SiLU) -> GemmA16Wx(up) -> Binary MUL  (qwen_v15.py:330-360)
+ * into one weight stream: the handle is created with N = intermediate size and desc.reserved = 1; both [K,N] weight
+ * sets are re-laid-out into one image (64 gate + 64 up channels per 128-row tile) and _run with
+ * activation = B2_ACT_SWIGLU writes C[m,n] = silu(alpha * a.Wg[:,n]) * (alpha * a.Wu[:,n]), C is [M, N].  No bias. */
+int b2_gemm_wq_prepare_swiglu(b2_gemm_wq_t handle, const void* q_gate, const void* s_gate, const void* z_gate,
+                              const void* q_up, const void* s_up, const void* z_up, void* stream);
 /* Use an image prepared by another handle with an identical desc (prefill/decode sharing). */
 int b2_gemm_wq_attach_packed(b2_gemm_wq_t handle, const void* packed, const void* scales_f32,
                              const void* zeros_f32);

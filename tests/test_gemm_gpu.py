@@ -134,3 +134,38 @@ def test_linearity_full_size():
     assert torch.count_nonzero(y0) == 0
     if exact:
         assert (y12 - (y1 + y2)).abs().max().item() <= 2e-2 * max(1.0, y12.abs().max().item())
+
+
+@pytest.mark.parametrize("wbits,group,M", [(4, -1, 1), (4, -1, 8), (4, -1, 64), (8, -1, 3), (4, 128, 5), (8, -1, 33), (16, -1, 2)])
+def test_fused_swiglu_pair(wbits, group, M):
+    """gate/up pair image + SwiGLU epilogue == silu(A.Wg) * (A.Wu) of the fp32 oracle (one rounding instead of three)."""
+    from b200spark import ops, quantize as PQ
+    K, N = 1024, 704  # N not a multiple of 64: exercises the padded tail tile
+    g = torch.Generator().manual_seed(M * 7 + wbits)
+    wg = (torch.randn(K, N, generator=g) * 0.02).to(torch.bfloat16)
+    wu = (torch.randn(K, N, generator=g) * 0.02).to(torch.bfloat16)
+    a = (torch.rand(M, K, generator=g) * 2 - 1).to(torch.bfloat16)
+    outs, refs = [], []
+    sets = []
+    for w in (wg, wu):
+        if wbits == 4:
+            q, s, z = PQ.quantize_a16w4(w, group); qu = Q.unpack_u4x2(q.numpy(), N)
+        elif wbits == 8:
+            q, s, z = PQ.quantize_a16w8(w, group); qu = q.numpy()
+        else:
+            q, s, z, qu = w, None, None, None
+        sets.append((q, s, z))
+        if wbits == 16:
+            refs.append(a.float().numpy().astype(np.float64) @ w.float().numpy().astype(np.float64))
+        else:
+            refs.append(Q.gemm_wq_math(a.float().numpy(), qu, s.float().numpy(), z.float().numpy(), group).astype(np.float64))
+    dev = lambda t: t.cuda() if t is not None else None
+    op = ops.GemmWQ(K, N, wbits, group, max_m=M, pair=True)
+    op.prepare_swiglu(*[dev(t) for t in sets[0]], *[dev(t) for t in sets[1]])
+    ws = ops.Workspace()
+    out = op(a.cuda(), ws)
+    out2 = op(a.cuda(), ws)
+    torch.cuda.synchronize()
+    assert out.shape == (M, N) and torch.equal(out, out2)
+    ref = (refs[0] / (1.0 + np.exp(-refs[0]))) * refs[1]
+    assert Q.err_min_abs_rel(ref.astype(np.float32), out.float().cpu().numpy()) <= TOL
