@@ -50,6 +50,12 @@ struct GemmParams {
   int nst_log2;     // log2(pipeline stages)
   int act;
   float alpha;
+  // optional RMSNorm fusion (b2_gemm_fuse)
+  const float* norm_sumsq;
+  const __nv_bfloat16* norm_gamma;
+  int norm_parts;
+  float norm_inv_hidden, norm_eps;
+  float* sumsq_out;
 };
 
 template <int WBITS>
@@ -146,7 +152,8 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
   float* fs = reinterpret_cast<float*>(xs + MP * XS);        // [MP][kBN] partial tile
   float* suma = fs + MP * kBN;                                // [MP][groups per chunk] (or [MP])
   const int gpc = GROUPED ? p.xt / gt : 1;                    // groups per chunk
-  uint64_t* full = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(suma + MP * gpc + 4) + 7) & ~uintptr_t(7));
+  float* sinv = suma + MP * gpc;                              // [MP] rsqrt(mean square) of the activation rows (norm fusion)
+  uint64_t* full = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sinv + MP + 4) + 7) & ~uintptr_t(7));
   uint64_t* empty = full + NST;
   __shared__ int s_is_last;
 
@@ -193,6 +200,17 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
 
   pdl_wait();  // activations / workspace / counters belong to the previous kernels from here on
 
+  if (p.norm_sumsq) {  // LayerNormNoBeta statistics from the producer's per-tile partial sums (fixed order)
+    for (int m = warp; m < MP; m += kWarps) {
+      float ss = 0.f;
+      if (m < p.M)
+        for (int i = lane; i < p.norm_parts; i += 32) ss += __ldcg(p.norm_sumsq + (size_t)i * p.M + m);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      if (lane == 0) sinv[m] = rsqrtf(ss * p.norm_inv_hidden + p.norm_eps);
+    }
+    named_bar_sync(1, kWarps * 32);
+  }
   const uint32_t w_ring = smem_u32(ring);
   // this thread's rows (16*warp + g, +8) inside the [chunk][row ^ swz][16B] tile image
   const int wc = WBITS == 4 ? (t >> 1) : (WBITS == 8 ? t : 2 * t);
@@ -220,7 +238,17 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
           float sacc = 0.f;
           for (int v = v0 + lane; v < v0 + gvec; v += 32) {
             uint4 val = make_uint4(0, 0, 0, 0);
-            if (mrow && kbase + v * 8 < p.K) val = *reinterpret_cast<const uint4*>(arow + v * 8);
+            if (mrow && kbase + v * 8 < p.K) {
+              val = *reinterpret_cast<const uint4*>(arow + v * 8);
+              if (p.norm_sumsq) {  // same fp32 op order and rounding as rmsnorm_kernel: (x * inv) * gamma -> bf16
+                const uint4 gv = *reinterpret_cast<const uint4*>(p.norm_gamma + kbase + v * 8);
+                const float inv = sinv[m];
+                val.x = pack_bf16x2(bf16_lo(val.x) * inv * bf16_lo(gv.x), bf16_hi(val.x) * inv * bf16_hi(gv.x));
+                val.y = pack_bf16x2(bf16_lo(val.y) * inv * bf16_lo(gv.y), bf16_hi(val.y) * inv * bf16_hi(gv.y));
+                val.z = pack_bf16x2(bf16_lo(val.z) * inv * bf16_lo(gv.z), bf16_hi(val.z) * inv * bf16_hi(gv.z));
+                val.w = pack_bf16x2(bf16_lo(val.w) * inv * bf16_lo(gv.w), bf16_hi(val.w) * inv * bf16_hi(gv.w));
+              }
+            }
             *reinterpret_cast<uint4*>(xrow + v * 16) = val;
             sacc += (bf16_lo(val.x) + bf16_hi(val.x)) + (bf16_lo(val.y) + bf16_hi(val.y)) +
                     (bf16_lo(val.z) + bf16_hi(val.z)) + (bf16_lo(val.w) + bf16_hi(val.w));
@@ -365,6 +393,25 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
     } else {
       cp[0] = __float2bfloat16(v0);
       if (has1) cp[1] = __float2bfloat16(v1);
+    }
+    if (p.sumsq_out) {  // keep what was actually stored (bf16-rounded) for the row statistics below
+      fs[m * kBN + np * 2] = __bfloat162float(__float2bfloat16(v0));
+      fs[m * kBN + np * 2 + 1] = has1 ? __bfloat162float(__float2bfloat16(v1)) : 0.f;
+    }
+  }
+  if (p.sumsq_out) {  // per-tile sum of squares of the output rows, for the next op's fused RMSNorm
+    named_bar_sync(1, kWarps * 32);
+    for (int m = warp; m < p.M; m += kWarps) {
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < kBN / 32; ++i) {
+        const int c = lane + 32 * i;
+        const float v = (ng * kBN + c) < p.N ? fs[m * kBN + c] : 0.f;
+        ss += v * v;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      if (lane == 0) p.sumsq_out[(size_t)ng * p.M + m] = ss;
     }
   }
 }
@@ -537,7 +584,7 @@ static int make_plan(b2_gemm_wq* h, int mti) {
   if (xt_cap < xq) xt_cap = xq;
   auto smem_for = [&](int xt) {
     const int gpc = grouped ? xt / gt : 1;
-    return nstage * stage_bytes_of(h->d.wbits) + MP * (xt * 128 + 16) + MP * kBN * 4 + MP * gpc * 4 + 16 + 8 + nstage * 16 + 64;
+    return nstage * stage_bytes_of(h->d.wbits) + MP * (xt * 128 + 16) + MP * kBN * 4 + MP * gpc * 4 + MP * 4 + 16 + 8 + nstage * 16 + 64;
   };
   // first guess occupancy with the cap, derive S, then shrink xt to what a unit really needs
   int smem = smem_for(xt_cap);
@@ -733,10 +780,21 @@ size_t b2_gemm_wq_algo_bytes(b2_gemm_wq_t h, int M) {
   return w + prm + (size_t)2 * M * ((size_t)d.K + d.N);
 }
 
+int b2_gemm_wq_sumsq_parts(b2_gemm_wq_t h) { return h ? h->NG : 0; }
+
 int b2_gemm_wq_run(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, int64_t ldc, int M, const void* bias,
                    const void* residual, int activation, float alpha, void* workspace, size_t workspace_bytes,
                    void* stream_) {
+  return b2_gemm_wq_run_fused(h, A, lda, C, ldc, M, bias, residual, activation, alpha, workspace, workspace_bytes, nullptr, stream_);
+}
+
+int b2_gemm_wq_run_fused(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, int64_t ldc, int M, const void* bias,
+                         const void* residual, int activation, float alpha, void* workspace, size_t workspace_bytes,
+                         const b2_gemm_fuse* fuse, void* stream_) {
   if (!h || !A || !C || M <= 0) return B2_ERR_PARAM;
+  const bool fused = fuse && (fuse->norm_sumsq || fuse->sumsq_out);
+  if (fused && (M > 16 || h->pair && fuse->sumsq_out)) return B2_ERR_UNSUPPORTED;
+  if (fuse && fuse->norm_sumsq && (!fuse->norm_gamma || fuse->norm_parts <= 0 || fuse->norm_hidden <= 0)) return B2_ERR_PARAM;
   if (!h->packed) return B2_ERR_RUNTIME;
   if (M > h->d.max_m) return B2_ERR_LIMIT;
   if (h->pair != (activation == B2_ACT_SWIGLU)) return B2_ERR_PARAM;  // paired image <=> SwiGLU epilogue
@@ -792,6 +850,12 @@ int b2_gemm_wq_run(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, int64_t 
     p.nst_log2 = pl.nst_log2;
     p.act = activation;
     p.alpha = alpha;
+    p.norm_sumsq = fuse ? fuse->norm_sumsq : nullptr;
+    p.norm_gamma = fuse ? (const __nv_bfloat16*)fuse->norm_gamma : nullptr;
+    p.norm_parts = fuse ? fuse->norm_parts : 0;
+    p.norm_inv_hidden = fuse && fuse->norm_hidden > 0 ? 1.0f / (float)fuse->norm_hidden : 0.f;
+    p.norm_eps = fuse ? fuse->norm_eps : 0.f;
+    p.sumsq_out = fuse ? fuse->sumsq_out : nullptr;
     gemm_kernel_t kern = pick_kernel(h->d.wbits, grouped, 1 << mti);
     cudaError_t e = launch(kern, dim3(h->NG * pl.S), dim3(kThreads), (size_t)pl.smem, stream, true, p);
     if (e != cudaSuccess) {

@@ -11,7 +11,8 @@ LIB_PATH = os.path.join(LIB_DIR, "libb200spark.so")
 SYMBOLS = [
     "b2_status_string", "b2_last_error", "b2_version", "b2_set_pdl",
     "b2_gemm_wq_create", "b2_gemm_wq_destroy", "b2_gemm_wq_packed_bytes", "b2_gemm_wq_prepare_weights",
-    "b2_gemm_wq_prepare_swiglu", "b2_gemm_wq_attach_packed", "b2_gemm_wq_workspace_bytes", "b2_gemm_wq_run", "b2_gemm_wq_algo_bytes",
+    "b2_gemm_wq_prepare_swiglu", "b2_gemm_wq_attach_packed", "b2_gemm_wq_workspace_bytes", "b2_gemm_wq_run", "b2_gemm_wq_run_fused", "b2_gemm_wq_sumsq_parts",
+    "b2_gemm_wq_algo_bytes",
     "b2_span_bytes", "b2_span_cache_append", "b2_span_attn_create", "b2_span_attn_destroy",
     "b2_span_attn_workspace_bytes", "b2_span_attn_run", "b2_span_attn_algo_bytes",
     "b2_rmsnorm", "b2_rotary", "b2_binary", "b2_embedding", "b2_argmax", "b2_argmax_shard", "b2_lens_add",
@@ -27,6 +28,11 @@ class SpanCfg(C.Structure):
     _fields_ = [("ft", C.c_int32), ("quant_mode", C.c_int32), ("n_heads", C.c_int32), ("n_groups", C.c_int32),
                 ("head_size", C.c_int32), ("span_len", C.c_int32), ("max_spans_per_seq", C.c_int32),
                 ("reserved", C.c_int32)]
+
+
+class GemmFuse(C.Structure):
+    _fields_ = [("norm_sumsq", C.c_void_p), ("norm_gamma", C.c_void_p), ("norm_parts", C.c_int32), ("norm_hidden", C.c_int32),
+                ("norm_eps", C.c_float), ("reserved", C.c_int32), ("sumsq_out", C.c_void_p)]
 
 
 class RopeCfg(C.Structure):
@@ -64,6 +70,8 @@ def _load():
         "b2_gemm_wq_attach_packed": (i32, [vp, vp, vp, vp]),
         "b2_gemm_wq_workspace_bytes": (sz, [vp, i32]),
         "b2_gemm_wq_run": (i32, [vp, vp, i64, vp, i64, i32, vp, vp, i32, f32, vp, sz, vp]),
+        "b2_gemm_wq_run_fused": (i32, [vp, vp, i64, vp, i64, i32, vp, vp, i32, f32, vp, sz, C.POINTER(GemmFuse), vp]),
+        "b2_gemm_wq_sumsq_parts": (i32, [vp]),
         "b2_gemm_wq_algo_bytes": (sz, [vp, i32]),
         "b2_span_bytes": (sz, [C.POINTER(SpanCfg)]),
         "b2_span_cache_append": (i32, [C.POINTER(SpanCfg), vp, vp, vp, vp, vp, i32, C.POINTER(RopeCfg), vp]),

@@ -118,7 +118,7 @@ class _RefView:
 
 class DecodeStack:
     def __init__(self, cfg, batch, max_len, wbits=4, group=-1, kv="none", span=128, seed=1234, device="cuda",
-                 keep_ref=False, layers=None, tp_rank=0, tp_size=1, tp_group=None, fuse_swiglu=True):
+                 keep_ref=False, layers=None, tp_rank=0, tp_size=1, tp_group=None, fuse_swiglu=True, fuse_norm=False):
         """tp_size > 1: the reference's tensor-parallel layout (QKV/gate/up column split, o/down row split + all-reduce,
         vocab-split lm_head + B-element all-gather); every rank builds the SAME full synthetic weights from `seed` and
         keeps its shard, exactly like the reference splits an already-quantized checkpoint."""
@@ -182,6 +182,14 @@ class DecodeStack:
             self.loc_val = torch.empty(batch, dtype=torch.float32, device=device)
             self.all_ids = torch.empty(tp, batch, dtype=torch.int64, device=device)
             self.all_val = torch.empty(tp, batch, dtype=torch.float32, device=device)
+        # RMSNorm fusion (decode batches <= 16, TP = 1): the row-parallel GEMVs emit per-tile sums of squares, their
+        # consumers normalise while staging activations; only layer 0's first norm stays a stand-alone kernel.
+        # Off by default: measured on B200 it removes 2 launches/layer but lengthens every GEMV's dependent chain
+        # (statistics load + barrier before staging) and loses ~4% at B=1 (438 vs 454 tok/s) — kept for the next round.
+        self.fuse_norm = fuse_norm and tp == 1 and batch <= 16
+        if self.fuse_norm:
+            self.ssq_o = torch.zeros(self.layers[0]["o"].op.sumsq_parts(), batch, dtype=torch.float32, device=device)
+            self.ssq_d = torch.zeros(self.layers[0]["down"].op.sumsq_parts(), batch, dtype=torch.float32, device=device)
         self.graph = None
         self.launches_per_step = 0
 
@@ -218,24 +226,40 @@ class DecodeStack:
 
     def _step_ops(self):
         cfg, ws = self.cfg, self.ws
+        H = cfg.hidden
+        fn = self.fuse_norm
         n = 0
         ops.embedding(self.embed, self.ids, out=self.x); n += 1
-        for L in self.layers:
-            ops.rmsnorm(self.x, L["g1"], cfg.eps, out=self.xn); n += 1
-            L["qkv"](self.xn, ws, out=self.qkv); n += 1
+        for li, L in enumerate(self.layers):
+            if fn and li > 0:  # x and its row statistics come from the previous layer's down_proj
+                L["qkv"](self.x, ws, out=self.qkv, norm_in=(self.ssq_d, L["g1"], H, cfg.eps)); n += 1
+            else:
+                ops.rmsnorm(self.x, L["g1"], cfg.eps, out=self.xn); n += 1
+                L["qkv"](self.xn, ws, out=self.qkv); n += 1
             ops.cache_append(L["cache"], self.qkv, self.lens_old, q_out=self.q, rope=self.rope); n += 1
             self.attn(self.q, L["cache"], self.lens_new, self.max_len, ws, out=self.ao); n += 1
-            n = self._row_parallel(L["o"], self.ao, n)
-            ops.rmsnorm(self.x, L["g2"], cfg.eps, out=self.xn); n += 1
-            if self.fuse_swiglu:
-                L["gateup"](self.xn, ws, out=self.gate); n += 1
+            if fn:
+                L["o"](self.ao, ws, out=self.x, residual=self.x, sumsq_out=self.ssq_o); n += 1
+                mlp_in, nin = self.x, (self.ssq_o, L["g2"], H, cfg.eps)
             else:
-                L["gate"](self.xn, ws, out=self.gate, act=ACT_SILU); n += 1
-                L["up"](self.xn, ws, out=self.up); n += 1
+                n = self._row_parallel(L["o"], self.ao, n)
+                ops.rmsnorm(self.x, L["g2"], cfg.eps, out=self.xn); n += 1
+                mlp_in, nin = self.xn, None
+            if self.fuse_swiglu:
+                L["gateup"](mlp_in, ws, out=self.gate, norm_in=nin); n += 1
+            else:
+                L["gate"](mlp_in, ws, out=self.gate, act=ACT_SILU, norm_in=nin); n += 1
+                L["up"](mlp_in, ws, out=self.up, norm_in=nin); n += 1
                 ops.binary(self.gate, self.up, BIN_MUL, out=self.gate); n += 1
-            n = self._row_parallel(L["down"], self.gate, n)
-        ops.rmsnorm(self.x, self.gf, cfg.eps, out=self.xn); n += 1
-        self.lm_head(self.xn, ws, out=self.logits); n += 1
+            if fn:
+                L["down"](self.gate, ws, out=self.x, residual=self.x, sumsq_out=self.ssq_d); n += 1
+            else:
+                n = self._row_parallel(L["down"], self.gate, n)
+        if fn:
+            self.lm_head(self.x, ws, out=self.logits, norm_in=(self.ssq_d, self.gf, H, cfg.eps)); n += 1
+        else:
+            ops.rmsnorm(self.x, self.gf, cfg.eps, out=self.xn); n += 1
+            self.lm_head(self.xn, ws, out=self.logits); n += 1
         if self.tp == 1:
             ops.argmax(self.logits, out=self.next_ids); n += 1
         else:  # vocab-split lm_head: local (max, argmax) + B-element all-gather instead of all-reducing 152064 logits

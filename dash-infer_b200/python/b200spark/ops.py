@@ -7,7 +7,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (ACT_NONE, BIN_ADD, BIN_MUL, DT_BF16, DT_I8, DT_U8, KV_I8, KV_NONE, KV_U4, GemmDesc, RopeCfg,
+from ._lib import (ACT_NONE, BIN_ADD, BIN_MUL, DT_BF16, DT_I8, DT_U8, KV_I8, KV_NONE, KV_U4, GemmDesc, GemmFuse, RopeCfg,
                    SpanCfg, check, lib)
 
 
@@ -74,7 +74,12 @@ class GemmWQ:
     def packed_bytes(self):
         return lib.b2_gemm_wq_packed_bytes(self.h)
 
-    def __call__(self, a, ws, out=None, act=ACT_NONE, alpha=1.0, residual=None):
+    def sumsq_parts(self):
+        return lib.b2_gemm_wq_sumsq_parts(self.h)
+
+    def __call__(self, a, ws, out=None, act=ACT_NONE, alpha=1.0, residual=None, norm_in=None, sumsq_out=None):
+        """norm_in = (sumsq [parts, M] fp32, gamma [K] bf16, hidden, eps): fused RMSNorm prologue;
+        sumsq_out [sumsq_parts(), M] fp32: per-tile row sums of squares of the output (for the next op's norm_in)."""
         if self.pair:
             act = _lib.ACT_SWIGLU
         M = a.numel() // a.shape[-1]
@@ -84,8 +89,19 @@ class GemmWQ:
         wsb = ws.reserve(self.workspace_bytes(M))
         lda = a.stride(-2) if a.dim() > 1 else self.K
         ldc = out.stride(-2) if out.dim() > 1 else self.N
-        check(lib.b2_gemm_wq_run(self.h, _ptr(a), lda, _ptr(out), ldc, M, _ptr(self.bias), _ptr(residual), act,
-                                 float(alpha), _ptr(wsb), wsb.numel(), _stream()), "b2_gemm_wq_run")
+        if norm_in is None and sumsq_out is None:
+            check(lib.b2_gemm_wq_run(self.h, _ptr(a), lda, _ptr(out), ldc, M, _ptr(self.bias), _ptr(residual), act,
+                                     float(alpha), _ptr(wsb), wsb.numel(), _stream()), "b2_gemm_wq_run")
+            return out
+        f = GemmFuse()
+        if norm_in is not None:
+            ss, gamma, hidden, eps = norm_in
+            f.norm_sumsq, f.norm_gamma = ss.data_ptr(), gamma.data_ptr()
+            f.norm_parts, f.norm_hidden, f.norm_eps = ss.shape[0], int(hidden), float(eps)
+        if sumsq_out is not None:
+            f.sumsq_out = sumsq_out.data_ptr()
+        check(lib.b2_gemm_wq_run_fused(self.h, _ptr(a), lda, _ptr(out), ldc, M, _ptr(self.bias), _ptr(residual), act,
+                                       float(alpha), _ptr(wsb), wsb.numel(), C.byref(f), _stream()), "b2_gemm_wq_run_fused")
         return out
 
     def __del__(self):

@@ -108,6 +108,24 @@ size_t b2_gemm_wq_workspace_bytes(b2_gemm_wq_t handle, int M);
 int b2_gemm_wq_run(b2_gemm_wq_t handle, const void* A, int64_t lda, void* C, int64_t ldc, int M,
                    const void* bias, const void* residual, int activation, float alpha,
                    void* workspace, size_t workspace_bytes, void* stream);
+/* RMSNorm fusion around the GEMV (decode batches <= 16; "next" row f2 of SURVEY.md §8): the producer of a hidden
+ * state (o_proj / down_proj with residual) also emits, per 128-channel tile, the sum of squares of each output row
+ * (sumsq_out [tiles][M], tiles = b2_gemm_wq_sumsq_parts); the consumer applies LayerNormNoBeta on the fly while staging
+ * its activations: a_norm[m,k] = A[m,k] * rsqrt(sum_p norm_sumsq[p][m] / norm_hidden + eps) * gamma[k], rounded to FT
+ * exactly like the stand-alone b2_rmsnorm.  Either half may be NULL.  Returns B2_ERR_UNSUPPORTED for M > 16. */
+typedef struct {
+  const float* norm_sumsq; /* [norm_parts][M] or NULL */
+  const void* norm_gamma;  /* [K] FT */
+  int32_t norm_parts;
+  int32_t norm_hidden;
+  float norm_eps;
+  int32_t reserved;
+  float* sumsq_out;        /* [b2_gemm_wq_sumsq_parts(handle)][M] or NULL */
+} b2_gemm_fuse;
+int b2_gemm_wq_sumsq_parts(b2_gemm_wq_t handle);
+int b2_gemm_wq_run_fused(b2_gemm_wq_t handle, const void* A, int64_t lda, void* C, int64_t ldc, int M,
+                         const void* bias, const void* residual, int activation, float alpha,
+                         void* workspace, size_t workspace_bytes, const b2_gemm_fuse* fuse, void* stream);
 /* Algorithmic bytes one run at this M must read from HBM (weights + params + A + C). */
 size_t b2_gemm_wq_algo_bytes(b2_gemm_wq_t handle, int M);
 

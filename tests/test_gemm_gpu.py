@@ -169,3 +169,40 @@ def test_fused_swiglu_pair(wbits, group, M):
     assert out.shape == (M, N) and torch.equal(out, out2)
     ref = (refs[0] / (1.0 + np.exp(-refs[0]))) * refs[1]
     assert Q.err_min_abs_rel(ref.astype(np.float32), out.float().cpu().numpy()) <= TOL
+
+
+@pytest.mark.parametrize("wbits,M", [(4, 1), (4, 8), (8, 3), (16, 16)])
+def test_fused_rmsnorm_prologue_and_sumsq_epilogue(wbits, M):
+    """producer GEMV (+residual, sumsq_out) -> consumer GEMV (norm_in) == producer -> b2_rmsnorm -> consumer."""
+    from b200spark import ops, quantize as PQ
+    H, N2 = 1024, 640
+    g = torch.Generator().manual_seed(wbits + M)
+    mk = lambda k, n: (torch.randn(k, n, generator=g) * 0.02).to(torch.bfloat16)
+    w1, w2 = mk(H, H), mk(H, N2)
+    a = (torch.rand(M, H, generator=g) * 2 - 1).to(torch.bfloat16).cuda()
+    res = (torch.randn(M, H, generator=g)).to(torch.bfloat16).cuda()
+    gamma = (1 + 0.1 * torch.randn(H, generator=g)).to(torch.bfloat16).cuda()
+
+    def lin(w, K, N):
+        if wbits == 4:
+            q, s, z = PQ.quantize_a16w4(w, -1)
+        elif wbits == 8:
+            q, s, z = PQ.quantize_a16w8(w, -1)
+        else:
+            q, s, z = w, None, None
+        d = lambda t: t.cuda() if t is not None else None
+        return ops.GemmWQ(K, N, wbits, -1, max_m=M).prepare(d(q), d(s), d(z))
+    p1, p2 = lin(w1, H, H), lin(w2, H, N2)
+    ws = ops.Workspace()
+    ssq = torch.zeros(p1.sumsq_parts(), M, dtype=torch.float32, device="cuda")
+    x = p1(a, ws, residual=res, sumsq_out=ssq)
+    x_plain = p1(a, ws, residual=res)
+    assert torch.equal(x, x_plain)
+    # the per-tile statistics sum to the row sums of squares of the stored bf16 values
+    assert torch.allclose(ssq.sum(0), x.float().pow(2).sum(-1), rtol=1e-5)
+    y_fused = p2(x, ws, norm_in=(ssq, gamma, H, 1e-6))
+    y_ref = p2(ops.rmsnorm(x, gamma, 1e-6), ws)
+    torch.cuda.synchronize()
+    # same rounding points; only the fp32 summation order of the mean square differs
+    assert (y_fused.float() - y_ref.float()).abs().max().item() <= 2e-2 * y_ref.float().abs().max().item()
+    assert (y_fused != y_ref).float().mean().item() < 0.05

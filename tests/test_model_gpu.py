@@ -45,6 +45,22 @@ def test_tiny_decoder_logits_and_tokens(wbits, group, kv):
     assert st.lens_old.cpu().tolist() == [steps] * B
 
 
+def test_fused_norm_stack_matches_unfused():
+    from b200spark import model
+    B = 2
+    a = model.DecodeStack(model.TINY, B, 64, wbits=4, span=16, seed=9, fuse_norm=True)
+    b = model.DecodeStack(model.TINY, B, 64, wbits=4, span=16, seed=9, fuse_norm=False)
+    assert a.fuse_norm and not b.fuse_norm
+    ids = torch.tensor([5, 6], dtype=torch.int64, device="cuda")
+    for t in range(4):
+        a.ids.copy_(ids); b.ids.copy_(ids)
+        a.step(); nb = b.step().clone()
+        torch.cuda.synchronize()
+        err = (a.logits.float() - b.logits.float()).abs().max().item()
+        assert err <= 1e-2 * b.logits.float().abs().max().item(), (t, err)
+        ids = nb
+
+
 def test_graph_replay_matches_eager():
     from b200spark import model
     B = 3
