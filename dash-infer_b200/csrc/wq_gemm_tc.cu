@@ -8,16 +8,19 @@
 //
 //   warp 0      : TMA producer — int4/int8 weight tiles (same init-time image as the mma.sync kernel) stream
 //                 HBM -> shared memory with cp.async.bulk, ahead of the previous kernel's completion (PDL)
-//   warps 2..5  : dequant — one thread per output channel: LDS.128 -> lop3/shf -> exact bf16 integers (16+q)
-//                 -> tcgen05.st into the A-operand region of TMEM (the dequantized weights never touch shared
-//                 memory: its bandwidth could not carry 2 B/weight at HBM rate)
+//   warps 2..5, : dequant — one thread per output channel: LDS.128 -> lop3/shf -> exact bf16 integers (16+q)
+//   warps 9..12   -> tcgen05.st into the A-operand region of TMEM (the dequantized weights never touch shared
+//                 memory: its bandwidth could not carry 2 B/weight at HBM rate).  Two groups of four warps take
+//                 alternate pipeline stages: one stage is a serial chain of barrier waits, LDS, ALU, tcgen05.st
+//                 and wait::st (~1000 clocks measured), two in flight hide it
 //   warp 8      : activation tiles (64 k x NM m) by TMA tensor-map loads into the 128B-swizzled K-major UMMA
 //                 layout (out-of-range rows/columns are zero-filled by the TMA unit)
 //   warps 6..7  : per-row sums sum_k a[m][k] needed by the zero-point term, read from the landed tiles
 //   warp 1      : one elected thread issues tcgen05.mma (A from TMEM, B from shared memory, D in TMEM) and
 //                 tcgen05.commit's the pipeline barriers
-//   epilogue    : warps 2..5 read D with tcgen05.ld, apply s * (acc - (16+z) * sum a), split-K partial or final
-//                 alpha/bias/activation/residual, bf16 store.
+//   epilogue    : the dequant warps read D with tcgen05.ld, apply s * (acc - (16+z) * sum a) and park the fp32 tile in
+//                 shared memory; then ALL 416 threads do the split-K partial store / last-CTA reduction and the final
+//                 alpha/bias/activation/residual with 16-byte reads and 8-byte bf16x4 stores.
 //
 // Roofline: HBM-bound up to M ~ 64 (256 FLOP/B ~ the tensor/HBM ridge); report both.
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
@@ -29,14 +32,15 @@
 
 namespace b2 {
 
-constexpr int kTcThreads = 288;      // warp 0 weights TMA, 1 MMA, 2-5 dequant/epilogue, 6-7 row sums, 8 activation TMA
+constexpr int kTcThreads = 416;      // warp 0 weights TMA, 1 MMA, 2-5 + 9-12 dequant (two groups, alternate stages), 6-7 row sums,
+                                     // 8 activation TMA; every warp joins the epilogue
 constexpr int kTcNM = 64;            // batch columns per MMA (UMMA N)
 constexpr int kTcNSW = 12;           // weight stages (8 KB each): ~2 us of HBM latency x 44 GB/s/SM needs >= 80 KB in flight
-constexpr int kTcNSX = 3;            // {dequantized-A buffer in TMEM, activation slot in smem} stages
+constexpr int kTcNSX = 4;            // {dequantized-A buffer in TMEM, activation slot in smem} stages
 constexpr int kTcXTile = kTcNM * 128;  // bytes: NM rows x 64 k bf16
 constexpr int kTcColsD = 0;          // TMEM columns [0, 64): accumulator
-constexpr int kTcColsA = 64;         // TMEM columns [64, 256): three A stages of 64 columns
-constexpr int kTcTmemCols = 256;
+constexpr int kTcColsA = 64;         // TMEM columns [64, 64 + 64 * NSX): the A stages, 64 columns each
+constexpr int kTcTmemCols = 512;
 
 // ---- tcgen05 wrappers (forms as in cute/arch/{mma_sm100_umma,copy_sm100,tmem_allocator_sm100}.hpp) ----
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -75,9 +79,19 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
 // optional timeline instrumentation (CTA 0 only): compiled in with -DB2_TC_TRACE
 #ifdef B2_TC_TRACE
 __device__ unsigned long long g_tc_trace[16][256];
+__device__ unsigned long long g_tc_gt[64][8];  // per launch (ring): globaltimer + clock at entry / end of CTA 0 and the last CTA
+__device__ __forceinline__ unsigned long long tc_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 #define TC_TRACE(role, idx) do { if (blockIdx.x == 0 && (idx) < 256) g_tc_trace[role][idx] = clock64(); } while (0)
+#define TC_GT(slot) do { if (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) { \
+    const int b_ = blockIdx.x == 0 ? 0 : 4; \
+    g_tc_gt[p.dbg & 63][b_ + (slot)] = tc_gtime(); } } while (0)
 #else
 #define TC_TRACE(role, idx) do {} while (0)
+#define TC_GT(slot) do {} while (0)
 #endif
 
 struct TcParams {
@@ -94,7 +108,16 @@ struct TcParams {
   int M, N, K, Np, KT, NG, S;
   int act;
   float alpha;
+  int dbg;  // ablation bitmask, only honoured when compiled with -DB2_TC_ABLATE (tools/tc_ablate.py)
 };
+
+// Timing-only ablations (results are wrong): 1 row sums skip their loads, 2 dequant skips everything, 4 no MMAs,
+// 8 no activation TMA, 16 dequant skips only the tcgen05.st, 32 no weight TMA
+#ifdef B2_TC_ABLATE
+#define TC_ABL(bit) ((p.dbg & (bit)) != 0)
+#else
+#define TC_ABL(bit) false
+#endif
 
 template <int WBITS>
 __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap amap) {
@@ -123,6 +146,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
   __shared__ int s_is_last;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) { TC_GT(0); TC_TRACE(7, 5); }
   const int ng = blockIdx.x / p.S;
   const int s = blockIdx.x - ng * p.S;
   const int kt0 = (int)((int64_t)s * p.KT / p.S), kt1 = (int)((int64_t)(s + 1) * p.KT / p.S);
@@ -157,6 +181,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
         const int slot = st % kTcNSW;
         if (st >= kTcNSW) mbar_wait_backoff(&wfree[slot], ((st / kTcNSW) & 1) ^ 1);
         const uint32_t bytes = min(TPS, nt - st * TPS) * TILE_BYTES;
+        if (TC_ABL(32)) { mbar_arrive(&wfull[slot]); continue; }
         mbar_arrive_expect_tx(&wfull[slot], bytes);
         bulk_g2s(wring + slot * WSTAGE, wsrc + (size_t)st * WSTAGE, bytes, &wfull[slot]);
         TC_TRACE(0, st);
@@ -166,6 +191,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
     // ===================== activation producer: TMA tensor-map loads (zero fill outside [M, K]) =====================
     if (lane == 0) {
       pdl_wait();  // A is the previous kernel's output
+      TC_GT(1); TC_TRACE(7, 6);
       for (int st = 0; st < nst; ++st) {
         const int slot = st % kTcNSX;
         if (st >= kTcNSX) {
@@ -176,6 +202,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
         const int tiles = min(TPS, nt - st * TPS);
         // the loads complete on the stage's 'ready' barrier (what the MMA thread waits for, together with the dequant
         // arrivals); the row-sum warps wait on the same barrier phase
+        if (TC_ABL(8)) { mbar_arrive(&afull[slot]); continue; }
         mbar_arrive_expect_tx(&afull[slot], tiles * kTcXTile);
         for (int ti = 0; ti < tiles; ++ti)
           asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -207,6 +234,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
               const uint64_t bdesc = desc_hi | (uint64_t)((((xaddr + kk * 32) >> 4) & 0x3FFF) | (1u << 16));
               const uint32_t acc = (st > 0 || ti > 0 || kk > 0) ? 1u : 0u;
               TC_TRACE(8 + ti * 4 + kk, st);
+              if (TC_ABL(4)) continue;
               if (WBITS == 4) {
                 tc_mma_ts(tmem + kTcColsD, tmem + kTcColsA + ab * ABUF + ti * ACOLS + kk * 8, bdesc, idesc, acc);
               } else {  // W8: per k16 step the buffer holds [lo plane | hi plane], 8 columns each
@@ -221,14 +249,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
         TC_TRACE(2, st);
       }
     }
-  } else if (warp >= 6) {
+  } else if (warp == 6 || warp == 7) {
     // ===================== row sums of the landed activation tiles (row = xt) =====================
     const int xt = tid - 192;  // 0..63
     float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
     for (int st = 0; st < nst; ++st) {
       const int slot = st % kTcNSX;
       mbar_wait(&afull[slot], (st / kTcNSX) & 1);  // stage ready (implies its activation tiles landed)
-      const int tiles = min(TPS, nt - st * TPS);
+      const int tiles = TC_ABL(1) ? 0 : min(TPS, nt - st * TPS);
       for (int ti = 0; ti < tiles; ++ti) {
         const uint32_t rbase = smem_u32(xring + slot * XSTAGE + ti * kTcXTile) + xt * 128;
 #pragma unroll
@@ -246,29 +274,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
       if (xt == 0) TC_TRACE(3, st);
     }
     suma[xt] = (r0 + r1) + (r2 + r3);
-    asm volatile("bar.sync 3, 192;" ::: "memory");  // hand the sums to the epilogue warps
+    asm volatile("bar.sync 3, 320;" ::: "memory");  // hand the sums to the dequant/epilogue warps
   } else {
-    // ===================== dequant (warps 2..5) then epilogue =====================
+    // ===================== dequant (warps 2..5: even stages, warps 9..12: odd stages), then TMEM -> smem =====================
+    const int grp = warp >= 9 ? 1 : 0;
     const int q = warp & 3;             // TMEM lane quadrant this warp may access
     const int r = q * 32 + lane;        // output channel (row of the 128-row tile)
     const float2 sz = p.sz[ng * kBN + r];  // per-channel (scale, zero + bias constant): immutable, read before the wait
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     const uint32_t wring_u = smem_u32(wring);
+    const bool tracer = tid == 64;
     uint32_t woff[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) woff[c] = c * 2048 + ((r ^ tile_swz(WBITS, c)) << 4);
 
-    for (int st = 0; st < nst; ++st) {
+    for (int st = grp; st < nst; st += 2) {
       const int slot = st % kTcNSW, ab = st % NAB;
       mbar_wait(&wfull[slot], (st / kTcNSW) & 1);
-      if (tid == 64) TC_TRACE(4, st);
+      if (tracer) TC_TRACE(4, st);
       if (st >= NAB) {  // A buffer ab was last read by stage st - NAB, whose commit went to mdone[(st - NAB) % NSX]
         const int ps = st - NAB;
         mbar_wait(&mdone[ps % kTcNSX], (ps / kTcNSX) & 1);
       }
       tc_fence_after();
-      if (tid == 64) TC_TRACE(5, st);
-      const int tiles = min(TPS, nt - st * TPS);
+      if (tracer) TC_TRACE(5, st);
+      const int tiles = TC_ABL(2) ? 0 : min(TPS, nt - st * TPS);
 #pragma unroll
       for (int ti = 0; ti < TPS; ++ti) {
         if (ti < tiles) {
@@ -290,7 +320,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
                   a[4 * jw + 2] = lop3_and_or(__funnelshift_r(w, w, 8), kMask4, kMagic);
                   a[4 * jw + 3] = lop3_and_or(__funnelshift_r(w, w, 12), kMask4, kMagic);
                 }
-                tc_st8(acol + (2 * c + h) * 8, a);
+                if (!TC_ABL(16)) tc_st8(acol + (2 * c + h) * 8, a);
+                else if (a[0] + a[3] + a[5] + a[7] == 0x12345u) tc_st8(acol, a);  // keep the ALU work alive
               }
             }
           } else {
@@ -316,132 +347,182 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (tid == 64) TC_TRACE(6, st);
+      if (tracer) TC_TRACE(6, st);
       if (lane == 0) {
         mbar_arrive(&wfree[slot]);
         mbar_arrive(&afull[ab]);
       }
     }
 
-    // ---------------- epilogue ----------------
-    pdl_wait();  // workspace / counters / C belong to the previous kernels until here
+    // ---------------- accumulators -> fp32 tile in shared memory (group g takes batch rows [32g, 32g + 32)) ----------------
     mbar_wait(dfull, 0);
-    if (tid == 64) TC_TRACE(7, 0);
+    if (tracer) TC_TRACE(7, 0);
     tc_fence_after();
-    asm volatile("bar.sync 3, 192;" ::: "memory");  // row sums ready
-    uint32_t d0[32], d1[32];
-    tc_ld32(trow + kTcColsD, d0);
-    tc_ld32(trow + kTcColsD + 32, d1);
-    tc_wait_ld();
-    // park the dequantized tile in shared memory ([m][128 n] fp32, over the drained weight ring): the rest of the
-    // epilogue is a small rolled loop (a 64x unrolled register epilogue thrashes the instruction cache)
-    float* fs = reinterpret_cast<float*>(wring);
+    asm volatile("bar.sync 3, 320;" ::: "memory");  // row sums ready
+    if (grp * 32 < p.M) {
+      uint32_t d[32];
+      tc_ld32(trow + kTcColsD + grp * 32, d);
+      tc_wait_ld();
+      if (tracer) TC_TRACE(7, 7);
+      // [m][128 n] fp32, over the drained weight ring (every weight stage has been consumed once dfull fired)
+      float* fsw = reinterpret_cast<float*>(wring) + (grp * 32) * kBN + r;
+      const float* sm = suma + grp * 32;
 #pragma unroll
-    for (int m = 0; m < 32; ++m) {
-      fs[m * kBN + r] = sz.x * (__uint_as_float(d0[m]) - sz.y * suma[m]);
-      fs[(m + 32) * kBN + r] = sz.x * (__uint_as_float(d1[m]) - sz.y * suma[m + 32]);
+      for (int m4 = 0; m4 < 32; m4 += 4) {
+        const float4 sa = *reinterpret_cast<const float4*>(sm + m4);
+        fsw[(m4 + 0) * kBN] = sz.x * (__uint_as_float(d[m4 + 0]) - sz.y * sa.x);
+        fsw[(m4 + 1) * kBN] = sz.x * (__uint_as_float(d[m4 + 1]) - sz.y * sa.y);
+        fsw[(m4 + 2) * kBN] = sz.x * (__uint_as_float(d[m4 + 2]) - sz.y * sa.z);
+        fsw[(m4 + 3) * kBN] = sz.x * (__uint_as_float(d[m4 + 3]) - sz.y * sa.w);
+      }
     }
-    asm volatile("bar.sync 4, 128;" ::: "memory");
-    const int et = tid - 64;  // 0..127
-    const int MPK = kTcNM * kBN;
+  }
+
+  // ======================= epilogue: all threads =======================
+  pdl_wait();  // workspace / counters / C belong to the previous kernels until here
+  tc_fence_before();
+  __syncthreads();  // tile parked
+  if (tid == 64) TC_TRACE(7, 1);
+  {
+    constexpr int T = kTcThreads;
+    const float4* fs4 = reinterpret_cast<const float4*>(wring);
+    float4* fs4w = reinterpret_cast<float4*>(wring);
+    const int units = p.M * (kBN / 4);  // float4 units, index = m * 32 + nq
+    constexpr int MPK4 = kTcNM * kBN / 4;
     bool finalize = true;
     if (p.S > 1) {
-      float* wsu = p.ws + ((size_t)ng * p.S + s) * MPK;
-      for (int i = et * 4; i < p.M * kBN; i += 128 * 4)
-        *reinterpret_cast<float4*>(wsu + i) = *reinterpret_cast<const float4*>(fs + i);
+      float4* wsu = reinterpret_cast<float4*>(p.ws) + ((size_t)ng * p.S + s) * MPK4;
+      for (int i = tid; i < units; i += T) wsu[i] = fs4[i];
       __threadfence();
-      asm volatile("bar.sync 4, 128;" ::: "memory");
-      if (et == 0) {
+      __syncthreads();
+      if (tid == 0) {
         const unsigned prev = atomicAdd(&p.counters[ng], 1u);
         s_is_last = (prev == (unsigned)(p.S - 1));
       }
-      asm volatile("bar.sync 4, 128;" ::: "memory");
+      __syncthreads();
       finalize = s_is_last != 0;
       if (finalize) {
         __threadfence();
-        const float* wsg = p.ws + (size_t)ng * p.S * MPK;
-        // fixed-order sum; 4 outputs x up to 8 partials = 32 independent 16-byte loads in flight per thread, so the
-        // whole reduction costs a handful of L2 round trips instead of one per output
-        const int lim = p.M * kBN;
-        for (int i0 = et * 4; i0 < lim; i0 += 128 * 4 * 4) {
-          float4 a[4];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) a[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // fixed-order sum over the S partials (deterministic); 2 units x 8 partials = 16 independent 16-byte loads in
+        // flight per thread, so the reduction is a few L2 round trips
+        const float4* wsg = reinterpret_cast<const float4*>(p.ws) + (size_t)ng * p.S * MPK4;
+        for (int i0 = tid; i0 < units; i0 += 2 * T) {
+          float4 a[2];
+          a[0] = a[1] = make_float4(0.f, 0.f, 0.f, 0.f);
           for (int s0 = 0; s0 < p.S; s0 += 8) {
-            float4 b[4][8];
+            float4 b[2][8];
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
+            for (int g = 0; g < 2; ++g)
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
-                const int i = i0 + g * 512;
-                b[g][u] = (s0 + u < p.S && i < lim) ? __ldcg(reinterpret_cast<const float4*>(wsg + (size_t)(s0 + u) * MPK + i))
-                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                const int i = i0 + g * T;
+                b[g][u] = (s0 + u < p.S && i < units) ? __ldcg(wsg + (size_t)(s0 + u) * MPK4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
               }
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
+            for (int g = 0; g < 2; ++g)
 #pragma unroll
               for (int u = 0; u < 8; ++u) { a[g].x += b[g][u].x; a[g].y += b[g][u].y; a[g].z += b[g][u].z; a[g].w += b[g][u].w; }
           }
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int i = i0 + g * 512;
-            if (i < lim) *reinterpret_cast<float4*>(fs + i) = a[g];
+          for (int g = 0; g < 2; ++g) {
+            const int i = i0 + g * T;
+            if (i < units) fs4w[i] = a[g];
           }
         }
-        if (et == 0) p.counters[ng] = 0;
-        asm volatile("bar.sync 4, 128;" ::: "memory");
+        if (tid == 0) p.counters[ng] = 0;  // re-arm for the next launch / graph replay
+        __syncthreads();
       }
     }
-    if (tid == 64) TC_TRACE(7, 1);
-    if (finalize && p.act == B2_ACT_SWIGLU) {  // tile = [64 gate | 64 up]: out[m, 64*ng + c] = silu(gate) * up
-      for (int i = et; i < p.M * 32; i += 128) {
-        const int m = i >> 5, np = i & 31;
-        const int nn = ng * 64 + np * 2;
-        if (nn >= p.N) continue;
-        const float g0 = fs[m * kBN + np * 2] * p.alpha, g1 = fs[m * kBN + np * 2 + 1] * p.alpha;
-        const float u0 = fs[m * kBN + 64 + np * 2] * p.alpha, u1 = fs[m * kBN + 64 + np * 2 + 1] * p.alpha;
-        const float v0 = apply_act<B2_ACT_SILU>(g0) * u0, v1 = apply_act<B2_ACT_SILU>(g1) * u1;
-        __nv_bfloat16* cp = p.C + (int64_t)m * p.ldc + nn;
-        if ((nn + 1) < p.N && ((reinterpret_cast<uintptr_t>(cp) & 3) == 0)) *reinterpret_cast<uint32_t*>(cp) = pack_bf16x2(v0, v1);
-        else {
-          cp[0] = __float2bfloat16(v0);
-          if ((nn + 1) < p.N) cp[1] = __float2bfloat16(v1);
+    if (tid == 64) TC_TRACE(7, 2);
+    if (finalize) {
+      const bool vec_ok = (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 7) == 0;
+      if (p.act == B2_ACT_SWIGLU) {
+        // tile = [64 gate | 64 up] channels: out[m, 64*ng + c] = silu(gate) * up; unit = 4 outputs
+        const int su = p.M * 16;
+#pragma unroll 1
+        for (int i = tid; i < su; i += T) {
+          const int m = i >> 4, nq = i & 15;
+          const int nn = ng * 64 + nq * 4;
+          if (nn >= p.N) continue;
+          const float4 gv = fs4[m * 32 + nq], uv = fs4[m * 32 + 16 + nq];
+          float v[4];
+          v[0] = apply_act<B2_ACT_SILU>(gv.x * p.alpha) * (uv.x * p.alpha);
+          v[1] = apply_act<B2_ACT_SILU>(gv.y * p.alpha) * (uv.y * p.alpha);
+          v[2] = apply_act<B2_ACT_SILU>(gv.z * p.alpha) * (uv.z * p.alpha);
+          v[3] = apply_act<B2_ACT_SILU>(gv.w * p.alpha) * (uv.w * p.alpha);
+          __nv_bfloat16* cp = p.C + (int64_t)m * p.ldc + nn;
+          if (vec_ok && nn + 3 < p.N) {
+            *reinterpret_cast<uint2*>(cp) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (nn + e < p.N) cp[e] = __float2bfloat16(v[e]);
+          }
         }
-      }
-    } else if (finalize) {
-#pragma unroll 4
-      for (int i = et; i < p.M * (kBN / 2); i += 128) {
-        const int m = i >> 6, np = i & 63;
-        const int nn = ng * kBN + np * 2;
-        if (nn >= p.N) continue;
-        float v0 = fs[m * kBN + np * 2] * p.alpha, v1 = fs[m * kBN + np * 2 + 1] * p.alpha;
-        const bool has1 = (nn + 1) < p.N;
-        if (p.bias) {
-          v0 += __bfloat162float(p.bias[nn]);
-          if (has1) v1 += __bfloat162float(p.bias[nn + 1]);
+      } else if (p.act == B2_ACT_NONE && vec_ok && (p.N & 3) == 0 &&
+                 (!p.residual || (reinterpret_cast<uintptr_t>(p.residual) & 7) == 0) &&
+                 (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 7) == 0)) {
+        // the decode-path case: no activation; all residual loads of a thread are issued before the first use
+        constexpr int UPT = (kTcNM * (kBN / 4) + T - 1) / T;  // units per thread (5)
+        uint2 res[UPT];
+#pragma unroll
+        for (int j = 0; j < UPT; ++j) {
+          const int i = tid + j * T;
+          const int m = i >> 5, nn = ng * kBN + (i & 31) * 4;
+          res[j] = make_uint2(0u, 0u);
+          if (p.residual && i < units && nn < p.N) res[j] = __ldg(reinterpret_cast<const uint2*>(p.residual + (int64_t)m * p.ldc + nn));
         }
-        v0 = apply_act_rt(v0, p.act);
-        v1 = apply_act_rt(v1, p.act);
-        __nv_bfloat16* cp = p.C + (int64_t)m * p.ldc + nn;
-        if (p.residual) {
-          const __nv_bfloat16* rp = p.residual + (int64_t)m * p.ldc + nn;
-          v0 += __bfloat162float(rp[0]);
-          if (has1) v1 += __bfloat162float(rp[1]);
+#pragma unroll
+        for (int j = 0; j < UPT; ++j) {
+          const int i = tid + j * T;
+          const int m = i >> 5, nn = ng * kBN + (i & 31) * 4;
+          if (i < units && nn < p.N) {
+            const float4 a = fs4[i];
+            float v0 = a.x * p.alpha, v1 = a.y * p.alpha, v2 = a.z * p.alpha, v3 = a.w * p.alpha;
+            if (p.bias) {
+              const uint2 bv = __ldg(reinterpret_cast<const uint2*>(p.bias + nn));
+              v0 += bf16_lo(bv.x); v1 += bf16_hi(bv.x); v2 += bf16_lo(bv.y); v3 += bf16_hi(bv.y);
+            }
+            v0 += bf16_lo(res[j].x); v1 += bf16_hi(res[j].x); v2 += bf16_lo(res[j].y); v3 += bf16_hi(res[j].y);
+            *reinterpret_cast<uint2*>(p.C + (int64_t)m * p.ldc + nn) = make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, v3));
+          }
         }
-        if (has1 && ((reinterpret_cast<uintptr_t>(cp) & 3) == 0)) {
-          *reinterpret_cast<uint32_t*>(cp) = pack_bf16x2(v0, v1);
-        } else {
-          cp[0] = __float2bfloat16(v0);
-          if (has1) cp[1] = __float2bfloat16(v1);
+      } else {
+        // generic: any activation / alignment (rolled on purpose: the inlined activation switch is large)
+        const float* fs = reinterpret_cast<const float*>(wring);
+#pragma unroll 1
+        for (int i = tid; i < p.M * (kBN / 2); i += T) {
+          const int m = i >> 6, np = i & 63;
+          const int nn = ng * kBN + np * 2;
+          if (nn >= p.N) continue;
+          float v0 = fs[m * kBN + np * 2] * p.alpha, v1 = fs[m * kBN + np * 2 + 1] * p.alpha;
+          const bool has1 = (nn + 1) < p.N;
+          if (p.bias) {
+            v0 += __bfloat162float(p.bias[nn]);
+            if (has1) v1 += __bfloat162float(p.bias[nn + 1]);
+          }
+          v0 = apply_act_rt(v0, p.act);
+          v1 = apply_act_rt(v1, p.act);
+          __nv_bfloat16* cp = p.C + (int64_t)m * p.ldc + nn;
+          if (p.residual) {
+            const __nv_bfloat16* rp = p.residual + (int64_t)m * p.ldc + nn;
+            v0 += __bfloat162float(rp[0]);
+            if (has1) v1 += __bfloat162float(rp[1]);
+          }
+          if (has1 && ((reinterpret_cast<uintptr_t>(cp) & 3) == 0)) {
+            *reinterpret_cast<uint32_t*>(cp) = pack_bf16x2(v0, v1);
+          } else {
+            cp[0] = __float2bfloat16(v0);
+            if (has1) cp[1] = __float2bfloat16(v1);
+          }
         }
       }
     }
   }
 
-  if (tid == 64) TC_TRACE(7, 2);
   tc_fence_before();
   __syncthreads();
-  if (tid == 0) TC_TRACE(7, 3);
+  if (tid == 0) { TC_TRACE(7, 3); TC_GT(2); }
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTcTmemCols) : "memory");
@@ -449,15 +530,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
 }
 
 #ifdef B2_TC_TRACE
+static unsigned g_tc_host_launches = 0;
 extern "C" int b2_debug_tc_trace(unsigned long long* host_out) {
   return (int)cudaMemcpyFromSymbol(host_out, g_tc_trace, sizeof(g_tc_trace));
+}
+extern "C" int b2_debug_tc_gt(unsigned long long* host_out, unsigned* launches) {
+  *launches = g_tc_host_launches;
+  return (int)cudaMemcpyFromSymbol(host_out, g_tc_gt, sizeof(g_tc_gt));
 }
 #endif
 
 int tc_smem_bytes(int wbits) {
   const int tps = wbits == 4 ? 2 : 1;
   const int wstage = tps * (wbits == 4 ? 4096 : 8192);
-  return 1024 + kTcNSX * tps * kTcXTile + kTcNSW * wstage + kTcNM * 4 + 40 * 8 + 64;
+  return 1024 + kTcNSX * tps * kTcXTile + kTcNSW * wstage + kTcNM * 4 + 48 * 8 + 64;
 }
 
 cudaError_t tc_configure(int wbits) {
@@ -498,6 +584,13 @@ cudaError_t tc_launch(int wbits, const TcLaunch& a, cudaStream_t stream) {
   p.packed = a.packed; p.sz = a.sz; p.A = a.A; p.lda = a.lda; p.C = a.C; p.ldc = a.ldc; p.bias = a.bias; p.residual = a.residual;
   p.ws = a.ws; p.counters = a.counters; p.M = a.M; p.N = a.N; p.K = a.K; p.Np = a.Np; p.KT = a.KT; p.NG = a.NG; p.S = a.S;
   p.act = a.act; p.alpha = a.alpha;
+  p.dbg = 0;
+#ifdef B2_TC_ABLATE
+  if (const char* e = getenv("B2_TC_ABLATE")) p.dbg = atoi(e);
+#endif
+#ifdef B2_TC_TRACE
+  p.dbg = (int)(g_tc_host_launches++);  // launch id (frozen into a captured graph node)
+#endif
   if (wbits == 4) return launch(wq_gemm_tc_kernel<4>, dim3(a.NG * a.S), dim3(kTcThreads), (size_t)tc_smem_bytes(4), stream, true, p, amap);
   return launch(wq_gemm_tc_kernel<8>, dim3(a.NG * a.S), dim3(kTcThreads), (size_t)tc_smem_bytes(8), stream, true, p, amap);
 }
