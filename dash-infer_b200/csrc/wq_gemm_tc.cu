@@ -35,11 +35,11 @@ namespace b2 {
 constexpr int kTcThreads = 416;      // warp 0 weights TMA, 1 MMA, 2-5 + 9-12 dequant (two groups, alternate stages), 6-7 row sums,
                                      // 8 activation TMA; every warp joins the epilogue
 constexpr int kTcNM = 64;            // batch columns per MMA (UMMA N)
-constexpr int kTcNSW = 12;           // weight stages (8 KB each): ~2 us of HBM latency x 44 GB/s/SM needs >= 80 KB in flight
-constexpr int kTcNSX = 4;            // {dequantized-A buffer in TMEM, activation slot in smem} stages
+constexpr int kTcNSW = 6;            // weight stages (16 KB each): ~2 us of HBM latency x 44 GB/s/SM needs >= 80 KB in flight
+constexpr int kTcNSX = 3;            // {dequantized-A buffer in TMEM, activation slot in smem} stages (128 columns / 32 or 16 KB each)
 constexpr int kTcXTile = kTcNM * 128;  // bytes: NM rows x 64 k bf16
 constexpr int kTcColsD = 0;          // TMEM columns [0, 64): accumulator
-constexpr int kTcColsA = 64;         // TMEM columns [64, 64 + 64 * NSX): the A stages, 64 columns each
+constexpr int kTcColsA = 64;         // TMEM columns [64, 64 + 128 * NSX): the A stages, 128 columns each
 constexpr int kTcTmemCols = 512;
 
 // ---- tcgen05 wrappers (forms as in cute/arch/{mma_sm100_umma,copy_sm100,tmem_allocator_sm100}.hpp) ----
@@ -123,12 +123,14 @@ template <int WBITS>
 __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap amap) {
   constexpr int TILE_BYTES = WBITS == 4 ? 4096 : 8192;
   constexpr int NCH = WBITS == 4 ? 2 : 4;      // 16B chunks per row per k-tile
-  constexpr int TPS = WBITS == 4 ? 2 : 1;      // k-tiles per pipeline stage (k128 for W4, k64 for W8)
+  // k-tiles per pipeline stage (k256 for W4, k128 for W8): one stage = 16 KB of weights = 16 tcgen05.mma per
+  // commit / barrier round trip of the issuing thread (that round trip costs ~400 clocks, an MMA 45)
+  constexpr int TPS = WBITS == 4 ? 4 : 2;
   constexpr int ACOLS = WBITS == 4 ? 32 : 64;  // TMEM columns of dequantized A per k-tile
-  constexpr int ABUF = ACOLS * TPS;            // per stage (64 columns)
+  constexpr int ABUF = ACOLS * TPS;            // per stage (128 columns)
   constexpr int NAB = kTcNSX;                  // A stages in TMEM == activation stages (one 'ready' barrier per stage)
-  constexpr int WSTAGE = TPS * TILE_BYTES;     // 8 KB
-  constexpr int XSTAGE = TPS * kTcXTile;       // 16 KB / 8 KB
+  constexpr int WSTAGE = TPS * TILE_BYTES;     // 16 KB
+  constexpr int XSTAGE = TPS * kTcXTile;       // 32 KB / 16 KB
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* xring = smem;                                   // NSX x XSTAGE, 1024B aligned (SWIZZLE_128B atoms)
@@ -167,7 +169,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  // warp-uniform for the compiler: tcgen05 operands then live in uniform registers (otherwise every tcgen05.mma is
+  // wrapped in an ELECT / R2UR.BROADCAST waterfall loop, ~70 clocks per MMA instead of the 45-clock hardware floor)
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   if (tid == 0) TC_TRACE(7, 4);
   pdl_launch_dependents();
 
@@ -229,17 +233,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
         for (int ti = 0; ti < TPS; ++ti) {
           if (ti < tiles) {
             const uint32_t xaddr = xbase + xs * XSTAGE + ti * kTcXTile;
+            // start-address field is (addr >> 4): a k16 step (32 B) inside the swizzle atom is +2
+            const uint64_t bdesc0 = desc_hi | (uint64_t)(((xaddr >> 4) & 0x3FFF) | (1u << 16));
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t bdesc = desc_hi | (uint64_t)((((xaddr + kk * 32) >> 4) & 0x3FFF) | (1u << 16));
+              const uint64_t bdesc = bdesc0 + (uint64_t)(2 * kk);
               const uint32_t acc = (st > 0 || ti > 0 || kk > 0) ? 1u : 0u;
-              TC_TRACE(8 + ti * 4 + kk, st);
+              if (ti * 4 + kk == TPS * 4 - 1) TC_TRACE(15, st);
               if (TC_ABL(4)) continue;
               if (WBITS == 4) {
                 tc_mma_ts(tmem + kTcColsD, tmem + kTcColsA + ab * ABUF + ti * ACOLS + kk * 8, bdesc, idesc, acc);
               } else {  // W8: per k16 step the buffer holds [lo plane | hi plane], 8 columns each
-                tc_mma_ts(tmem + kTcColsD, tmem + kTcColsA + ab * ABUF + kk * 16, bdesc, idesc, acc);
-                tc_mma_ts(tmem + kTcColsD, tmem + kTcColsA + ab * ABUF + kk * 16 + 8, bdesc, idesc, 1u);
+                tc_mma_ts(tmem + kTcColsD, tmem + kTcColsA + ab * ABUF + ti * ACOLS + kk * 16, bdesc, idesc, acc);
+                tc_mma_ts(tmem + kTcColsD, tmem + kTcColsA + ab * ABUF + ti * ACOLS + kk * 16 + 8, bdesc, idesc, 1u);
               }
             }
           }
@@ -541,7 +547,7 @@ extern "C" int b2_debug_tc_gt(unsigned long long* host_out, unsigned* launches) 
 #endif
 
 int tc_smem_bytes(int wbits) {
-  const int tps = wbits == 4 ? 2 : 1;
+  const int tps = wbits == 4 ? 4 : 2;
   const int wstage = tps * (wbits == 4 ? 4096 : 8192);
   return 1024 + kTcNSX * tps * kTcXTile + kTcNSW * wstage + kTcNM * 4 + 48 * 8 + 64;
 }

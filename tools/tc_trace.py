@@ -51,4 +51,4 @@ nt = max(i for i in range(256) if t[2][i]) + 1
 print("clocks from entry: setup_done", t[7][4] - t0, "pdl_ready", t[7][6] - t0, "dfull", t[7][0] - t0, "tmem_loaded", t[7][7] - t0,
       "parked", t[7][1] - t0, "reduced", t[7][2] - t0, "end", t[7][3] - t0, "stages", nt)
 for j in range(nt):
-    print(j, " ".join(f"{names[r]}={t[r][j] - t0:7d}" for r in range(7)), "| mma issue deltas", [t[8 + i][j] - t[1][j] for i in range(8)])
+    print(j, " ".join(f"{names[r]}={t[r][j] - t0:7d}" for r in range(7)), "| last mma issue at +%d" % (t[15][j] - t[1][j]))
