@@ -822,7 +822,7 @@ static int mt_index_for(int M) { return M <= 8 ? 0 : (M <= 16 ? 1 : 2); }
 
 static bool use_tc(const b2_gemm_wq* h, int M) {
   static const int min_m = env_int("B2_GEMM_TC_MIN_M", 17);
-  return h->d.wbits != 16 && h->group_tiles == 0 && M >= min_m;
+  return h->group_tiles == 0 && M >= min_m;  // int4 / int8 per-channel and dense bf16 (lm_head)
 }
 
 static int make_tc_plan(b2_gemm_wq* h) {

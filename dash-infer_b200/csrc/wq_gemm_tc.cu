@@ -121,12 +121,13 @@ struct TcParams {
 
 template <int WBITS>
 __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap amap) {
-  constexpr int TILE_BYTES = WBITS == 4 ? 4096 : 8192;
-  constexpr int NCH = WBITS == 4 ? 2 : 4;      // 16B chunks per row per k-tile
+  constexpr int TILE_BYTES = WBITS == 4 ? 4096 : (WBITS == 8 ? 8192 : 16384);
+  constexpr int NCH = WBITS == 4 ? 2 : (WBITS == 8 ? 4 : 8);  // 16B chunks per row per k-tile
+  constexpr int NSW = WBITS == 16 ? 4 : kTcNSW;               // weight stages (bf16: 32 KB each)
   // k-tiles per pipeline stage (k256 for W4, k128 for W8): one stage = 16 KB of weights = 16 tcgen05.mma per
   // commit / barrier round trip of the issuing thread (that round trip costs ~400 clocks, an MMA 45)
   constexpr int TPS = WBITS == 4 ? 4 : 2;
-  constexpr int ACOLS = WBITS == 4 ? 32 : 64;  // TMEM columns of dequantized A per k-tile
+  constexpr int ACOLS = WBITS == 8 ? 64 : 32;  // TMEM columns of dequantized A per k-tile (int8: lo and hi planes)
   constexpr int ABUF = ACOLS * TPS;            // per stage (128 columns)
   constexpr int NAB = kTcNSX;                  // A stages in TMEM == activation stages (one 'ready' barrier per stage)
   constexpr int WSTAGE = TPS * TILE_BYTES;     // 16 KB
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* xring = smem;                                   // NSX x XSTAGE, 1024B aligned (SWIZZLE_128B atoms)
   uint8_t* wring = xring + kTcNSX * XSTAGE;                // NSW x WSTAGE
-  float* suma = reinterpret_cast<float*>(wring + kTcNSW * WSTAGE);  // [NM]
+  float* suma = reinterpret_cast<float*>(wring + NSW * WSTAGE);  // [NM]
   uint64_t* bars = reinterpret_cast<uint64_t*>(suma + kTcNM);
   uint64_t* wfull = bars;                 // [NSW] weights landed (TMA tx)
   uint64_t* wfree = wfull + kTcNSW;       // [NSW] dequant warps done with the smem stage (4 arrivals)
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
   const int nst = (nt + TPS - 1) / TPS;  // pipeline stages of this unit
 
   if (tid == 0) {
-    for (int i = 0; i < kTcNSW; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wfree[i], 4); }
+    for (int i = 0; i < NSW; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wfree[i], 4); }
     // xfull: TMA tx (sum warps wait on it); ready: TMA tx + 4 dequant-warp arrivals (the MMA thread waits on it)
     for (int i = 0; i < kTcNSX; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xsum[i], 2); mbar_init(&mdone[i], 1); mbar_init(&afull[i], 5); }
     mbar_init(dfull, 1);
@@ -182,8 +183,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
     if (lane == 0) {
       const uint8_t* wsrc = p.packed + ((size_t)ng * p.KT + kt0) * TILE_BYTES;
       for (int st = 0; st < nst; ++st) {
-        const int slot = st % kTcNSW;
-        if (st >= kTcNSW) mbar_wait_backoff(&wfree[slot], ((st / kTcNSW) & 1) ^ 1);
+        const int slot = st % NSW;
+        if (st >= NSW) mbar_wait_backoff(&wfree[slot], ((st / NSW) & 1) ^ 1);
         const uint32_t bytes = min(TPS, nt - st * TPS) * TILE_BYTES;
         if (TC_ABL(32)) { mbar_arrive(&wfull[slot]); continue; }
         mbar_arrive_expect_tx(&wfull[slot], bytes);
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
               const uint32_t acc = (st > 0 || ti > 0 || kk > 0) ? 1u : 0u;
               if (ti * 4 + kk == TPS * 4 - 1) TC_TRACE(15, st);
               if (TC_ABL(4)) continue;
-              if (WBITS == 4) {
+              if (WBITS != 8) {
                 tc_mma_ts(tmem + kTcColsD, tmem + kTcColsA + ab * ABUF + ti * ACOLS + kk * 8, bdesc, idesc, acc);
               } else {  // W8: per k16 step the buffer holds [lo plane | hi plane], 8 columns each
                 tc_mma_ts(tmem + kTcColsD, tmem + kTcColsA + ab * ABUF + ti * ACOLS + kk * 16, bdesc, idesc, acc);
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
     for (int st = 0; st < nst; ++st) {
       const int slot = st % kTcNSX;
       mbar_wait(&afull[slot], (st / kTcNSX) & 1);  // stage ready (implies its activation tiles landed)
-      const int tiles = TC_ABL(1) ? 0 : min(TPS, nt - st * TPS);
+      const int tiles = (TC_ABL(1) || WBITS == 16) ? 0 : min(TPS, nt - st * TPS);  // bf16 weights: no zero-point term
       for (int ti = 0; ti < tiles; ++ti) {
         const uint32_t rbase = smem_u32(xring + slot * XSTAGE + ti * kTcXTile) + xt * 128;
 #pragma unroll
@@ -286,7 +287,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
     const int grp = warp >= 9 ? 1 : 0;
     const int q = warp & 3;             // TMEM lane quadrant this warp may access
     const int r = q * 32 + lane;        // output channel (row of the 128-row tile)
-    const float2 sz = p.sz[ng * kBN + r];  // per-channel (scale, zero + bias constant): immutable, read before the wait
+    // per-channel (scale, zero + bias constant): immutable, read before the wait
+    const float2 sz = WBITS == 16 ? make_float2(1.f, 0.f) : p.sz[ng * kBN + r];
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     const uint32_t wring_u = smem_u32(wring);
     const bool tracer = tid == 64;
@@ -295,8 +297,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
     for (int c = 0; c < NCH; ++c) woff[c] = c * 2048 + ((r ^ tile_swz(WBITS, c)) << 4);
 
     for (int st = grp; st < nst; st += 2) {
-      const int slot = st % kTcNSW, ab = st % NAB;
-      mbar_wait(&wfull[slot], (st / kTcNSW) & 1);
+      const int slot = st % NSW, ab = st % NAB;
+      mbar_wait(&wfull[slot], (st / NSW) & 1);
       if (tracer) TC_TRACE(4, st);
       if (st >= NAB) {  // A buffer ab was last read by stage st - NAB, whose commit went to mdone[(st - NAB) % NSX]
         const int ps = st - NAB;
@@ -329,6 +331,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
                 if (!TC_ABL(16)) tc_st8(acol + (2 * c + h) * 8, a);
                 else if (a[0] + a[3] + a[5] + a[7] == 0x12345u) tc_st8(acol, a);  // keep the ALU work alive
               }
+            }
+          } else if (WBITS == 16) {  // bf16 weights: a plain copy, k16 step kk = chunks 2kk, 2kk+1
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint4 w0 = lds128(wt + woff[2 * kk]), w1 = lds128(wt + woff[2 * kk + 1]);
+              const uint32_t a[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+              tc_st8(acol + kk * 8, a);
             }
           } else {
 #pragma unroll
@@ -548,12 +557,14 @@ extern "C" int b2_debug_tc_gt(unsigned long long* host_out, unsigned* launches) 
 
 int tc_smem_bytes(int wbits) {
   const int tps = wbits == 4 ? 4 : 2;
-  const int wstage = tps * (wbits == 4 ? 4096 : 8192);
-  return 1024 + kTcNSX * tps * kTcXTile + kTcNSW * wstage + kTcNM * 4 + 48 * 8 + 64;
+  const int wstage = tps * (wbits == 4 ? 4096 : (wbits == 8 ? 8192 : 16384));
+  const int nsw = wbits == 16 ? 4 : kTcNSW;
+  return 1024 + kTcNSX * tps * kTcXTile + nsw * wstage + kTcNM * 4 + 48 * 8 + 64;
 }
 
 cudaError_t tc_configure(int wbits) {
   if (wbits == 4) return cudaFuncSetAttribute(wq_gemm_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(4));
+  if (wbits == 16) return cudaFuncSetAttribute(wq_gemm_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(16));
   return cudaFuncSetAttribute(wq_gemm_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(8));
 }
 
@@ -598,6 +609,7 @@ cudaError_t tc_launch(int wbits, const TcLaunch& a, cudaStream_t stream) {
   p.dbg = (int)(g_tc_host_launches++);  // launch id (frozen into a captured graph node)
 #endif
   if (wbits == 4) return launch(wq_gemm_tc_kernel<4>, dim3(a.NG * a.S), dim3(kTcThreads), (size_t)tc_smem_bytes(4), stream, true, p, amap);
+  if (wbits == 16) return launch(wq_gemm_tc_kernel<16>, dim3(a.NG * a.S), dim3(kTcThreads), (size_t)tc_smem_bytes(16), stream, true, p, amap);
   return launch(wq_gemm_tc_kernel<8>, dim3(a.NG * a.S), dim3(kTcThreads), (size_t)tc_smem_bytes(8), stream, true, p, amap);
 }
 

@@ -106,6 +106,12 @@ def test_qwen2_7b_w8_and_g128():
     _run(4, 4096, 6144, 32, 128, seed=42)  # Llama-3-8B QKV, GPTQ g128, batch 32
 
 
+def test_dense_bf16_tcgen05_multiwave():
+    """bf16 weights on the tcgen05 path (lm_head shape class): more n-groups than SMs, ragged N tail, M 17..64."""
+    _run(16, 3584, 19000, 64, -1, seed=71)
+    _run(16, 1024, 4100, 23, -1, seed=72, use_bias=True, act=5)
+
+
 def test_forced_split_paths(monkeypatch):
     monkeypatch.setenv("B2_GEMM_FORCE_SPLIT", "1")
     _run(4, 1024, 256, 2, -1, seed=51)
@@ -146,7 +152,7 @@ def test_linearity_full_size():
         assert (y12 - (y1 + y2)).abs().max().item() <= 2e-2 * max(1.0, y12.abs().max().item())
 
 
-@pytest.mark.parametrize("wbits,group,M", [(4, -1, 1), (4, -1, 8), (4, -1, 64), (8, -1, 3), (4, 128, 5), (8, -1, 33), (16, -1, 2)])
+@pytest.mark.parametrize("wbits,group,M", [(4, -1, 1), (4, -1, 8), (4, -1, 64), (8, -1, 3), (4, 128, 5), (8, -1, 33), (16, -1, 2), (16, -1, 40)])
 @pytest.mark.parametrize("cl", [0, 16])
 def test_fused_swiglu_pair(wbits, group, M, cl, monkeypatch):
     """gate/up pair image + SwiGLU epilogue == silu(A.Wg) * (A.Wu) of the fp32 oracle (one rounding instead of three)."""

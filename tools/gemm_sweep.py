@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.join(ROOT, "dash-infer_b200", "python"))
 import torch  # noqa: E402
 from b200spark import ops, quantize as PQ, lib  # noqa: E402
 
-SHAPES = {"gate": (3584, 18944), "down": (18944, 3584), "qkv": (3584, 4608), "o": (3584, 3584)}
+SHAPES = {"gate": (3584, 18944), "down": (18944, 3584), "qkv": (3584, 4608), "o": (3584, 3584), "lm": (3584, 152064)}
 
 
 def bench(K, N, M, wbits=4, nw=8, rounds=20, env=None, pdl=1):
@@ -72,5 +72,5 @@ if __name__ == "__main__":
             for M in ms:
                 for env in envs:
                     e2 = dict(env); pdl = int(e2.pop('PDL', 1))
-                    us, gbs = bench(K, N, M, env=e2, nw=nw, pdl=pdl)
+                    us, gbs = bench(K, N, M, wbits=int(os.environ.get('SWEEP_WBITS', '4')), env=e2, nw=nw, pdl=pdl)
                     print(f"{name:5s} M={M} env={env}: {us:7.2f} us  {gbs:7.1f} GB/s", flush=True)
