@@ -119,7 +119,8 @@ struct TcParams {
 #define TC_ABL(bit) false
 #endif
 
-template <int WBITS>
+// MULTI: a CTA walks several units (more units than SMs); the single-unit instantiation folds the unit loop away
+template <int WBITS, bool MULTI>
 __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap amap) {
   constexpr int TILE_BYTES = WBITS == 4 ? 4096 : (WBITS == 8 ? 8192 : 16384);
   constexpr int NCH = WBITS == 4 ? 2 : (WBITS == 8 ? 4 : 8);  // 16B chunks per row per k-tile
@@ -150,11 +151,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) { TC_GT(0); TC_TRACE(7, 5); }
-  const int ng = blockIdx.x / p.S;
-  const int s = blockIdx.x - ng * p.S;
-  const int kt0 = (int)((int64_t)s * p.KT / p.S), kt1 = (int)((int64_t)(s + 1) * p.KT / p.S);
-  const int nt = kt1 - kt0;
-  const int nst = (nt + TPS - 1) / TPS;  // pipeline stages of this unit
+  const int nunits = p.NG * p.S;
 
   if (tid == 0) {
     for (int i = 0; i < NSW; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wfree[i], 4); }
@@ -176,31 +173,61 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
   if (tid == 0) TC_TRACE(7, 4);
   pdl_launch_dependents();
 
-  // Stage st uses weight slot st % NSW, X slot st % NSX, A buffer st % NAB; mdone[st % NSX] is committed once the
-  // tensor core has consumed stage st (NSX is a multiple of NAB, so its phase also tells when the A buffer is free).
+  // Persistent over work units (n-group, k-split): unit = blockIdx.x, += gridDim.x.  Barriers, TMEM and the ring phases carry
+  // over; g = gbase + st is the stage index since kernel start.  Stage g uses weight slot g % NSW, X slot g % NSX, A buffer
+  // g % NAB; mdone[g % NSX] is committed once the tensor core has consumed stage g (NSX == NAB, so its phase also tells when
+  // the A buffer is free).
+  int w_pre = 0;  // weight stages of the current unit already issued during the previous unit's tail (producer thread only)
+  // (loop control and everything the tcgen05.mma operands derive from must stay provably warp-uniform: see `tmem`)
+  const int my_units = !MULTI ? 1 : ((int)blockIdx.x < nunits) ? (nunits - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  for (int uit = 0; uit < my_units; ++uit) {
+  const int unit = (int)blockIdx.x + uit * (int)gridDim.x;
+  const int ng = unit / p.S;
+  const int s = unit - ng * p.S;
+  const int kt0 = (int)((int64_t)s * p.KT / p.S), kt1 = (int)((int64_t)(s + 1) * p.KT / p.S);
+  const int nt = kt1 - kt0;
+  const int nst = (nt + TPS - 1) / TPS;  // pipeline stages of this unit
+  // stages before this unit.  A CTA only walks several units when S == 1, where every unit has the same stage count; a
+  // closed form (not a loop-carried sum) keeps the value provably warp-uniform for the tcgen05.mma operands
+  const int gbase = MULTI ? uit * nst : 0;
   if (warp == 0) {
     // ===================== weight producer (does not wait for the previous kernel) =====================
     if (lane == 0) {
-      const uint8_t* wsrc = p.packed + ((size_t)ng * p.KT + kt0) * TILE_BYTES;
-      for (int st = 0; st < nst; ++st) {
-        const int slot = st % NSW;
-        if (st >= NSW) mbar_wait_backoff(&wfree[slot], ((st / NSW) & 1) ^ 1);
-        const uint32_t bytes = min(TPS, nt - st * TPS) * TILE_BYTES;
-        if (TC_ABL(32)) { mbar_arrive(&wfull[slot]); continue; }
+      auto issue = [&](int g, const uint8_t* src, uint32_t bytes) {
+        const int slot = g % NSW;
+        if (g >= NSW) mbar_wait_backoff(&wfree[slot], ((g / NSW) & 1) ^ 1);
+        if (TC_ABL(32)) { mbar_arrive(&wfull[slot]); return; }
         mbar_arrive_expect_tx(&wfull[slot], bytes);
-        bulk_g2s(wring + slot * WSTAGE, wsrc + (size_t)st * WSTAGE, bytes, &wfull[slot]);
-        TC_TRACE(0, st);
+        bulk_g2s(wring + slot * WSTAGE, src, bytes, &wfull[slot]);
+      };
+      const uint8_t* wsrc = p.packed + ((size_t)ng * p.KT + kt0) * TILE_BYTES;
+      for (int st = w_pre; st < nst; ++st) {
+        issue(gbase + st, wsrc + (size_t)st * WSTAGE, min(TPS, nt - st * TPS) * TILE_BYTES);
+        TC_TRACE(0, gbase + st);
+      }
+      // head of the next unit: its first stages stream in while this unit drains and runs its epilogue
+      w_pre = 0;
+      const int nu = unit + gridDim.x;
+      if (MULTI && nu < nunits) {
+        const int ng2 = nu / p.S, s2 = nu - ng2 * p.S;
+        const int k0 = (int)((int64_t)s2 * p.KT / p.S), k1 = (int)((int64_t)(s2 + 1) * p.KT / p.S);
+        const int nt2 = k1 - k0, nst2 = (nt2 + TPS - 1) / TPS;
+        const uint8_t* wsrc2 = p.packed + ((size_t)ng2 * p.KT + k0) * TILE_BYTES;
+        w_pre = min(NSW, nst2);
+        for (int st = 0; st < w_pre; ++st)
+          issue(gbase + nst + st, wsrc2 + (size_t)st * WSTAGE, min(TPS, nt2 - st * TPS) * TILE_BYTES);
       }
     }
   } else if (warp == 8) {
     // ===================== activation producer: TMA tensor-map loads (zero fill outside [M, K]) =====================
     if (lane == 0) {
       pdl_wait();  // A is the previous kernel's output
-      TC_GT(1); TC_TRACE(7, 6);
+      if (uit == 0) { TC_GT(1); TC_TRACE(7, 6); }
       for (int st = 0; st < nst; ++st) {
-        const int slot = st % kTcNSX;
-        if (st >= kTcNSX) {
-          const uint32_t par = ((st / kTcNSX) & 1) ^ 1;
+        const int g = gbase + st;
+        const int slot = g % kTcNSX;
+        if (g >= kTcNSX) {
+          const uint32_t par = ((g / kTcNSX) & 1) ^ 1;
           mbar_wait_backoff(&mdone[slot], par);
           mbar_wait_backoff(&xsum[slot], par);
         }
@@ -218,18 +245,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
     }
   } else if (warp == 1) {
     // ===================== MMA issuer: a single thread =====================
+    // re-broadcast what the tcgen05.mma operands derive from: outer-loop values are not provably warp-uniform for the
+    // compiler, and a non-uniform operand costs an R2UR waterfall per MMA (see `tmem`)
+    const int gb = __shfl_sync(0xffffffffu, gbase, 0);
+    const int nst_u = __shfl_sync(0xffffffffu, nst, 0), nt_u = __shfl_sync(0xffffffffu, nt, 0);
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N = NM, M = 128 (cute::UMMA::InstrDescriptor)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcNM >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       // B smem descriptor (cute::UMMA::SmemDescriptor): K-major, SWIZZLE_128B, SBO = 1024 B (8-row groups), version 1
       const uint64_t desc_hi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
       const uint32_t xbase = smem_u32(xring);
-      for (int st = 0; st < nst; ++st) {
-        const int ab = st % NAB, xs = st % kTcNSX;
-        mbar_wait(&afull[ab], (st / NAB) & 1);  // dequantized A stored in TMEM and activations landed
+      for (int st = 0; st < nst_u; ++st) {
+        const int g = gb + st;
+        const int ab = g % NAB, xs = g % kTcNSX;
+        mbar_wait(&afull[ab], (g / NAB) & 1);  // dequantized A stored in TMEM and activations landed
         tc_fence_after();
-        TC_TRACE(1, st);
-        const int tiles = min(TPS, nt - st * TPS);
+        TC_TRACE(1, g);
+        const int tiles = min(TPS, nt_u - st * TPS);
 #pragma unroll
         for (int ti = 0; ti < TPS; ++ti) {
           if (ti < tiles) {
@@ -240,7 +272,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
             for (int kk = 0; kk < 4; ++kk) {
               const uint64_t bdesc = bdesc0 + (uint64_t)(2 * kk);
               const uint32_t acc = (st > 0 || ti > 0 || kk > 0) ? 1u : 0u;
-              if (ti * 4 + kk == TPS * 4 - 1) TC_TRACE(15, st);
+              if (ti * 4 + kk == TPS * 4 - 1) TC_TRACE(15, g);
               if (TC_ABL(4)) continue;
               if (WBITS != 8) {
                 tc_mma_ts(tmem + kTcColsD, tmem + kTcColsA + ab * ABUF + ti * ACOLS + kk * 8, bdesc, idesc, acc);
@@ -252,8 +284,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
           }
         }
         tc_commit(&mdone[xs]);
-        if (st == nst - 1) tc_commit(dfull);
-        TC_TRACE(2, st);
+        if (st == nst_u - 1) tc_commit(dfull);
+        TC_TRACE(2, g);
       }
     }
   } else if (warp == 6 || warp == 7) {
@@ -261,8 +293,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
     const int xt = tid - 192;  // 0..63
     float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
     for (int st = 0; st < nst; ++st) {
-      const int slot = st % kTcNSX;
-      mbar_wait(&afull[slot], (st / kTcNSX) & 1);  // stage ready (implies its activation tiles landed)
+      const int g = gbase + st;
+      const int slot = g % kTcNSX;
+      mbar_wait(&afull[slot], (g / kTcNSX) & 1);  // stage ready (implies its activation tiles landed)
       const int tiles = (TC_ABL(1) || WBITS == 16) ? 0 : min(TPS, nt - st * TPS);  // bf16 weights: no zero-point term
       for (int ti = 0; ti < tiles; ++ti) {
         const uint32_t rbase = smem_u32(xring + slot * XSTAGE + ti * kTcXTile) + xt * 128;
@@ -278,7 +311,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&xsum[slot]);
-      if (xt == 0) TC_TRACE(3, st);
+      if (xt == 0) TC_TRACE(3, g);
     }
     suma[xt] = (r0 + r1) + (r2 + r3);
     asm volatile("bar.sync 3, 320;" ::: "memory");  // hand the sums to the dequant/epilogue warps
@@ -296,16 +329,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
 #pragma unroll
     for (int c = 0; c < NCH; ++c) woff[c] = c * 2048 + ((r ^ tile_swz(WBITS, c)) << 4);
 
-    for (int st = grp; st < nst; st += 2) {
-      const int slot = st % NSW, ab = st % NAB;
-      mbar_wait(&wfull[slot], (st / NSW) & 1);
-      if (tracer) TC_TRACE(4, st);
-      if (st >= NAB) {  // A buffer ab was last read by stage st - NAB, whose commit went to mdone[(st - NAB) % NSX]
-        const int ps = st - NAB;
+    for (int st = (grp ^ gbase) & 1; st < nst; st += 2) {  // group = parity of the global stage index
+      const int g = gbase + st;
+      const int slot = g % NSW, ab = g % NAB;
+      mbar_wait(&wfull[slot], (g / NSW) & 1);
+      if (tracer) TC_TRACE(4, g);
+      if (g >= NAB) {  // A buffer ab was last read by stage g - NAB, whose commit went to mdone[(g - NAB) % NSX]
+        const int ps = g - NAB;
         mbar_wait(&mdone[ps % kTcNSX], (ps / kTcNSX) & 1);
       }
       tc_fence_after();
-      if (tracer) TC_TRACE(5, st);
+      if (tracer) TC_TRACE(5, g);
       const int tiles = TC_ABL(2) ? 0 : min(TPS, nt - st * TPS);
 #pragma unroll
       for (int ti = 0; ti < TPS; ++ti) {
@@ -362,7 +396,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (tracer) TC_TRACE(6, st);
+      if (tracer) TC_TRACE(6, g);
       if (lane == 0) {
         mbar_arrive(&wfree[slot]);
         mbar_arrive(&afull[ab]);
@@ -370,7 +404,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
     }
 
     // ---------------- accumulators -> fp32 tile in shared memory (group g takes batch rows [32g, 32g + 32)) ----------------
-    mbar_wait(dfull, 0);
+    mbar_wait(dfull, uit & 1);
     if (tracer) TC_TRACE(7, 0);
     tc_fence_after();
     asm volatile("bar.sync 3, 320;" ::: "memory");  // row sums ready
@@ -379,8 +413,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
       tc_ld32(trow + kTcColsD + grp * 32, d);
       tc_wait_ld();
       if (tracer) TC_TRACE(7, 7);
-      // [m][128 n] fp32, over the drained weight ring (every weight stage has been consumed once dfull fired)
-      float* fsw = reinterpret_cast<float*>(wring) + (grp * 32) * kBN + r;
+      // [m][128 n] fp32, over the drained activation ring (all of this unit's MMAs have completed once dfull fired; the
+      // weight ring is already receiving the next unit's first stages)
+      float* fsw = reinterpret_cast<float*>(xring) + (grp * 32) * kBN + r;
       const float* sm = suma + grp * 32;
 #pragma unroll
       for (int m4 = 0; m4 < 32; m4 += 4) {
@@ -400,8 +435,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
   if (tid == 64) TC_TRACE(7, 1);
   {
     constexpr int T = kTcThreads;
-    const float4* fs4 = reinterpret_cast<const float4*>(wring);
-    float4* fs4w = reinterpret_cast<float4*>(wring);
+    const float4* fs4 = reinterpret_cast<const float4*>(xring);
+    float4* fs4w = reinterpret_cast<float4*>(xring);
     const int units = p.M * (kBN / 4);  // float4 units, index = m * 32 + nq
     constexpr int MPK4 = kTcNM * kBN / 4;
     bool finalize = true;
@@ -504,7 +539,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
         }
       } else {
         // generic: any activation / alignment (rolled on purpose: the inlined activation switch is large)
-        const float* fs = reinterpret_cast<const float*>(wring);
+        const float* fs = reinterpret_cast<const float*>(xring);
 #pragma unroll 1
         for (int i = tid; i < p.M * (kBN / 2); i += T) {
           const int m = i >> 6, np = i & 63;
@@ -536,7 +571,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (MULTI) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy tile writes before the next unit's TMA writes
+  __syncthreads();  // the tile in the X ring and the accumulator are free again
+  tc_fence_after();
+  }  // unit loop
+
   if (tid == 0) { TC_TRACE(7, 3); TC_GT(2); }
   if (warp == 1) {
     tc_fence_after();
@@ -563,9 +602,12 @@ int tc_smem_bytes(int wbits) {
 }
 
 cudaError_t tc_configure(int wbits) {
-  if (wbits == 4) return cudaFuncSetAttribute(wq_gemm_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(4));
-  if (wbits == 16) return cudaFuncSetAttribute(wq_gemm_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(16));
-  return cudaFuncSetAttribute(wq_gemm_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(8));
+  cudaError_t e = cudaSuccess;
+  auto cfg = [&](auto kern) { if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(wbits)); };
+  if (wbits == 4) { cfg(wq_gemm_tc_kernel<4, false>); cfg(wq_gemm_tc_kernel<4, true>); }
+  else if (wbits == 16) { cfg(wq_gemm_tc_kernel<16, false>); cfg(wq_gemm_tc_kernel<16, true>); }
+  else { cfg(wq_gemm_tc_kernel<8, false>); cfg(wq_gemm_tc_kernel<8, true>); }
+  return e;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -608,9 +650,20 @@ cudaError_t tc_launch(int wbits, const TcLaunch& a, cudaStream_t stream) {
 #ifdef B2_TC_TRACE
   p.dbg = (int)(g_tc_host_launches++);  // launch id (frozen into a captured graph node)
 #endif
-  if (wbits == 4) return launch(wq_gemm_tc_kernel<4>, dim3(a.NG * a.S), dim3(kTcThreads), (size_t)tc_smem_bytes(4), stream, true, p, amap);
-  if (wbits == 16) return launch(wq_gemm_tc_kernel<16>, dim3(a.NG * a.S), dim3(kTcThreads), (size_t)tc_smem_bytes(16), stream, true, p, amap);
-  return launch(wq_gemm_tc_kernel<8>, dim3(a.NG * a.S), dim3(kTcThreads), (size_t)tc_smem_bytes(8), stream, true, p, amap);
+  // persistent: one CTA per SM walks the (n-group, k-split) units; B2_GEMM_TC_PERSIST=0 launches one CTA per unit
+  static const int persist = [] { const char* e = getenv("B2_GEMM_TC_PERSIST"); return e ? atoi(e) : 1; }();
+  const int units = a.NG * a.S;
+  const int grid = (persist && units > sm_count()) ? sm_count() : units;
+  const bool multi = units > grid;
+  const size_t smem = (size_t)tc_smem_bytes(wbits);
+  if (wbits == 4)
+    return multi ? launch(wq_gemm_tc_kernel<4, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap)
+                 : launch(wq_gemm_tc_kernel<4, false>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap);
+  if (wbits == 16)
+    return multi ? launch(wq_gemm_tc_kernel<16, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap)
+                 : launch(wq_gemm_tc_kernel<16, false>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap);
+  return multi ? launch(wq_gemm_tc_kernel<8, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap)
+               : launch(wq_gemm_tc_kernel<8, false>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap);
 }
 
 }  // namespace b2

@@ -112,6 +112,14 @@ def test_dense_bf16_tcgen05_multiwave():
     _run(16, 1024, 4100, 23, -1, seed=72, use_bias=True, act=5)
 
 
+def test_tcgen05_persistent_units():
+    """More (n-group, k-split) units than SMs: every CTA walks several units (ring phases, accumulator and the parked tile
+    carry over; the next unit's weights are prefetched during the epilogue)."""
+    _run(4, 1024, 128 * 300 + 50, 33, -1, seed=73, use_res=True)
+    _run(8, 512, 128 * 450, 64, -1, seed=74, use_bias=True)
+    _run(16, 1024, 128 * 400 + 8, 64, -1, seed=75)
+
+
 def test_forced_split_paths(monkeypatch):
     monkeypatch.setenv("B2_GEMM_FORCE_SPLIT", "1")
     _run(4, 1024, 256, 2, -1, seed=51)
