@@ -182,40 +182,48 @@ def run_gpu(args):
         io = {"gate": (xn, st.gate), "gateup": (xn, st.gate), "up": (xn, st.up), "qkv": (xn, st.qkv), "o": (st.ao, st.x),
               "down": (st.gate, st.x)}
 
-        def gemm_entry(name, key, act=0):
+        nl = len(st.layers)
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        except Exception:
+            tj = {}
+
+        def entry(name, t, nb, per_step, tkey, note=None):
+            e = {"us": round(t * 1e6, 2), "GBps": round(nb / t / 1e9, 1), "frac": round(nb / t / 1e9 / hbm_peak, 3),
+                 "algo_bytes": nb, "launches_per_step": per_step, "traffic": tj.get("%s B=%d" % (tkey, B))}
+            if note:
+                e["note"] = note
+            kern[name] = e
+
+        def gemm_entry(name, key, tkey, act=0):
             src, dst = io[key]
             fns = [(lambda L=L: L[key](src, ws, out=dst, act=act)) for L in st.layers]
             t = time_kernel_loop(fns, rounds, torch)
-            nb = st.layers[0][key].op.algo_bytes(B)
-            kern[name] = {"us": round(t * 1e6, 2), "GBps": round(nb / t / 1e9, 1), "frac": round(nb / t / 1e9 / hbm_peak, 3),
-                          "algo_bytes": nb}
+            entry(name, t, st.layers[0][key].op.algo_bytes(B), nl, tkey)
         fused = st.fuse_swiglu
-        dom = "wq_gemm[gate+up SwiGLU %dx2x%d]" % (cfg.hidden, cfg.inter) if fused else "wq_gemm[gate %dx%d]" % (cfg.hidden, cfg.inter)
-        gemm_entry(dom, "gateup" if fused else "gate", 0 if fused else ACT_SILU)
-        gemm_entry("wq_gemm[down %dx%d]" % (cfg.inter, cfg.hidden), "down")
-        gemm_entry("wq_gemm[qkv %dx%d]" % (cfg.hidden, (cfg.n_heads + 2 * cfg.n_kv) * 128), "qkv")
-        gemm_entry("wq_gemm[o %dx%d]" % (cfg.n_heads * 128, cfg.hidden), "o")
+        if fused:
+            gemm_entry("wq_gemm[gate+up SwiGLU %dx2x%d]" % (cfg.hidden, cfg.inter), "gateup", "wq_gemm[gate+up]")
+        else:
+            gemm_entry("wq_gemm[gate %dx%d]" % (cfg.hidden, cfg.inter), "gate", "wq_gemm[gate]", ACT_SILU)
+            gemm_entry("wq_gemm[up %dx%d]" % (cfg.hidden, cfg.inter), "up", "wq_gemm[up]")
+        gemm_entry("wq_gemm[down %dx%d]" % (cfg.inter, cfg.hidden), "down", "wq_gemm[down]")
+        gemm_entry("wq_gemm[qkv %dx%d]" % (cfg.hidden, (cfg.n_heads + 2 * cfg.n_kv) * 128), "qkv", "wq_gemm[qkv]")
+        gemm_entry("wq_gemm[o %dx%d]" % (cfg.n_heads * 128, cfg.hidden), "o", "wq_gemm[o]")
         cur = int(st.lens_new[0].item())
         fns = [(lambda L=L: st.attn(st.q, L["cache"], st.lens_new, st.max_len, ws, out=st.ao)) for L in st.layers]
         t = time_kernel_loop(fns, rounds, torch)
-        nb = st.attn.algo_bytes(B * cur)
-        kern["span_attn[B=%d,ctx=%d]" % (B, cur)] = {"us": round(t * 1e6, 2), "GBps": round(nb / t / 1e9, 1),
-                                                      "frac": round(nb / t / 1e9 / hbm_peak, 3), "algo_bytes": nb}
+        entry("span_attn[B=%d,ctx=%d]" % (B, cur), t, st.attn.algo_bytes(B * cur), nl, "span_attn")
         t = time_kernel_loop([lambda: st.lm_head(xn, ws, out=st.logits)], 10, torch)
-        nb = st.lm_head.op.algo_bytes(B)
-        kern["wq_gemm[lm_head bf16 %dx%d]" % (cfg.hidden, cfg.vocab)] = {"us": round(t * 1e6, 2), "GBps": round(nb / t / 1e9, 1),
-                                                                         "frac": round(nb / t / 1e9 / hbm_peak, 3), "algo_bytes": nb,
-                                                                         "note": "same weights every launch; 1.09 GB >> L2"}
-        traffic = None
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-            key = ("wq_gemm_tc[gate+up] M=64" if B > 16 else "wq_gemm[gate+up] M<=16") if fused else \
-                  ("wq_gemm_tc[gate] M=64" if B > 16 else "wq_gemm[gate] M<=16")
-            traffic = tj.get(key)
-        except Exception:
-            pass
+        entry("wq_gemm[lm_head bf16 %dx%d]" % (cfg.hidden, cfg.vocab), t, st.lm_head.op.algo_bytes(B), 1, "wq_gemm[lm_head]",
+              note="same weights every launch; 1.09 GB >> L2")
+        # the dominant kernel = the largest share of the step's kernel time (us x launches per step)
+        tot = sum(v["us"] * v["launches_per_step"] for v in kern.values())
+        for v in kern.values():
+            v["share_of_kernel_time"] = round(v["us"] * v["launches_per_step"] / tot, 3)
+        dom = max(kern, key=lambda k: kern[k]["share_of_kernel_time"])
         roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["GBps"], "peak": hbm_peak, "unit": "GB/s",
-                "frac": kern[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                "frac": kern[dom]["frac"], "traffic": kern[dom]["traffic"], "peak_source": peak_src,
+                "share_of_kernel_time": kern[dom]["share_of_kernel_time"],
                 "step": {"algo_bytes": step_bytes, "weights_bytes": wbytes, "kv_bytes": kvbytes,
                          "GBps": round(step_bytes / (ms * 1e-3 / K) / 1e9, 1),
                          "frac": round(step_bytes / (ms * 1e-3 / K) / 1e9 / hbm_peak, 3),
@@ -274,9 +282,11 @@ def run_reference(args):
     from oracle import decoder_ref as DR
     cfg = {"qwen2-7b": model.QWEN2_7B, "llama3-8b": model.LLAMA3_8B, "tiny": model.TINY}[args.model]
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    threads = os.cpu_count()
+    # torch's default intra-op pool = one thread per physical core; measured on the GPU box: forcing every hyperthread
+    # (os.cpu_count() = 128) makes the oneDNN bf16 matmuls ~30x slower than the 64-thread default, which would be an
+    # unfairly slow baseline
     r = DR.time_cpu_decode(cfg, args.batch, args.ctx, sample_layers=2, steps=max(1, min(args.steps, 4)),
-                           warmup=max(1, min(args.warmup, 2)), threads=threads)
+                           warmup=max(1, min(args.warmup, 2)), threads=None)
     v = round(r["tokens_per_s"], 3)
     sample = ("2 of %d decoder layers + lm_head per step (per-layer time x %d + head), bf16 oneDNN matmul via torch CPU, fp32 "
               "contiguous KV at ctx %d, batch %d" % (cfg.layers, cfg.layers, args.ctx, args.batch))

@@ -1,12 +1,13 @@
 """Summarise an .ncu-rep (ncu --set full) into markdown for profiles/.
-usage: python tools/ncu_summary.py rep.ncu-rep "title" algo_bytes_per_launch [event_time_us] > profiles/x.md"""
+usage: python tools/ncu_summary.py rep.ncu-rep "title" algo_bytes[,algo_bytes...] [event_us[,event_us...]] > profiles/x.md"""
 import csv
 import subprocess
 import sys
 
 rep, title = sys.argv[1], sys.argv[2]
-algo = float(sys.argv[3]) if len(sys.argv) > 3 else None
-ev_us = float(sys.argv[4]) if len(sys.argv) > 4 else None
+# algorithmic bytes / CUDA-event times: one value, or a comma list in kernel order ("-" to skip an entry)
+algos = [None if a in ("-", "") else float(a) for a in sys.argv[3].split(",")] if len(sys.argv) > 3 else []
+evs = [None if a in ("-", "") else float(a) for a in sys.argv[4].split(",")] if len(sys.argv) > 4 else []
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
@@ -19,8 +20,10 @@ keys = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 print(f"# {title}\n")
 print(f"Source: `{rep.split('/')[-1]}` (`ncu --set full --clock-control none --import-source on`, one GPU, B200). "
       "Durations under ncu are cold-cache and serialised; the bench number is the CUDA-event time in bench.py.\n")
-for row in rows[2:]:
+for ki, row in enumerate(rows[2:]):
     name = row[hdr.index("Kernel Name")]
+    algo = (algos[ki] if ki < len(algos) else None) if len(algos) != 1 else algos[0]
+    ev_us = (evs[ki] if ki < len(evs) else None) if len(evs) != 1 else evs[0]
     print(f"## `{name}`\n")
     print("| metric | value | unit |\n|---|---|---|")
     vals = {}
@@ -32,7 +35,7 @@ for row in rows[2:]:
     try:
         rd = float(vals["dram__bytes_read.sum"].replace(",", "")); wr = float(vals["dram__bytes_write.sum"].replace(",", ""))
         ru, wu = units[hdr.index("dram__bytes_read.sum")], units[hdr.index("dram__bytes_write.sum")]
-        mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
         traffic = rd * mult.get(ru, 1) + wr * mult.get(wu, 1)
         dur = float(vals["gpu__time_duration.sum"].replace(",", "")) * {"us": 1e-6, "ms": 1e-3, "ns": 1e-9, "s": 1}[units[hdr.index("gpu__time_duration.sum")]]
         print(f"\nDRAM traffic (read+write) per launch: **{traffic / 1e6:.2f} MB**", end="")

@@ -34,7 +34,10 @@ torch.cuda.profiler.start()
 for _ in range(a.iters):
     if a.what == "gemm":
         for L in st.layers:
-            L["gate"](st.xn, st.ws, out=st.gate, act=ACT_SILU)
+            if st.fuse_swiglu:
+                L["gateup"](st.xn, st.ws, out=st.gate)
+            else:
+                L["gate"](st.xn, st.ws, out=st.gate, act=ACT_SILU)
             L["down"](st.gate, st.ws, out=st.x)
             L["qkv"](st.xn, st.ws, out=st.qkv)
             L["o"](st.ao, st.ws, out=st.x)
