@@ -56,7 +56,6 @@ struct GemmParams {
   int norm_parts;
   float norm_inv_hidden, norm_eps;
   float* sumsq_out;
-  int cluster;  // 1: the S split-K CTAs of an n-group form a thread-block cluster and reduce through DSMEM
 };
 
 template <int WBITS>
@@ -181,11 +180,6 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
         mbar_arrive_expect_tx(&full[slot], bytes);
         bulk_g2s(ring + slot * T::STAGE_BYTES, wsrc + (size_t)i * T::STAGE_BYTES, bytes, &full[slot]);
       }
-    }
-    if (p.cluster) {  // every thread of every CTA takes part in the two cluster barriers of the DSMEM reduction
-      __syncwarp();
-      cluster_sync_all();
-      cluster_sync_all();
     }
     return;
   }
@@ -325,70 +319,6 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
 
   const int ctid = tid;
   const int MPK = MP * kBN;
-  if (p.cluster) {
-    // ---- split-K reduction through distributed shared memory: no global workspace, no fence, no atomic.
-    //      CTA s of the cluster finalises a 1/S slice of the tile.  Every (unit, rank) partial is fetched by its own
-    //      thread so all DSMEM loads of a CTA are in flight at once (one remote round trip), parked in the (now idle)
-    //      weight ring, then summed in rank order (deterministic).
-    cluster_sync_all();  // every CTA's partial tile is parked in its shared memory
-    const bool swi = p.act == B2_ACT_SWIGLU;
-    const int V = swi ? 2 : 1;                 // float4 vectors per unit (SwiGLU: gate quad + matching up quad)
-    const int upr = swi ? 16 : 32;             // units per tile row
-    const int U = p.M * upr;
-    const int per = (U + p.S - 1) / p.S;
-    const int u0 = s * per;
-    const int cnt = max(0, min(U, u0 + per) - u0);
-    const int vecs = cnt * V;
-    float4* red = reinterpret_cast<float4*>(ring);  // [rank][vecs]
-    const uint32_t fs_u32 = smem_u32(fs);
-    for (int i = ctid; i < vecs * p.S; i += kWarps * 32) {
-      const int r = i / vecs, j = i - r * vecs;
-      const int u = u0 + (swi ? (j >> 1) : j), v = swi ? (j & 1) : 0;
-      const int m = u / upr, q = u - m * upr;
-      red[i] = ld_dsmem_f4(dsmem_addr(fs_u32 + (m * kBN + v * 64 + q * 4) * 4, r));
-    }
-    named_bar_sync(1, kWarps * 32);
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");  // done reading the peers' tiles
-    for (int j = ctid; j < cnt; j += kWarps * 32) {
-      const int u = u0 + j;
-      const int m = u / upr, q = u - m * upr;
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int r = 0; r < p.S; ++r) {
-        const float4 x = red[r * vecs + j * V];
-        a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
-        if (swi) {
-          const float4 y = red[r * vecs + j * V + 1];
-          b.x += y.x; b.y += y.y; b.z += y.z; b.w += y.w;
-        }
-      }
-      float v[4] = {a.x * p.alpha, a.y * p.alpha, a.z * p.alpha, a.w * p.alpha};
-      const int n = (swi ? ng * 64 : ng * kBN) + q * 4;
-      if (swi) {
-        const float w[4] = {b.x * p.alpha, b.y * p.alpha, b.z * p.alpha, b.w * p.alpha};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = apply_act<B2_ACT_SILU>(v[e]) * w[e];
-      } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if (n + e < p.N) {
-            if (p.bias) v[e] += __bfloat162float(p.bias[n + e]);
-            v[e] = apply_act_rt(v[e], p.act);
-            if (p.residual) v[e] += __bfloat162float(p.residual[(int64_t)m * p.ldc + n + e]);
-          }
-        }
-      }
-      __nv_bfloat16* cp = p.C + (int64_t)m * p.ldc + n;
-      if (n + 3 < p.N && ((reinterpret_cast<uintptr_t>(cp) & 7) == 0)) {
-        *reinterpret_cast<uint2*>(cp) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
-      } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (n + e < p.N) cp[e] = __float2bfloat16(v[e]);
-      }
-    }
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");  // nobody exits while a peer may still read its tile
-    return;
-  }
   if (p.S > 1) {
     float* wsu = p.ws + ((size_t)ng * p.S + s) * MPK;
     for (int i = ctid * 4; i < p.M * kBN; i += kWarps * 32 * 4)
@@ -592,7 +522,6 @@ using namespace b2;
 struct Plan {
   bool valid = false;
   int S = 1, xt = 1, smem = 0, quanta = 1, nst_log2 = 2;
-  bool cluster = false;
 };
 
 struct b2_gemm_wq {
@@ -604,7 +533,7 @@ struct b2_gemm_wq {
   float2* sz = nullptr;
   bool own_sz = false;
   unsigned* counters = nullptr;
-  Plan plans[6];  // MT = 1, 2, 4; [3..5]: the same without the cluster reduction (needed by the sumsq_out epilogue)
+  Plan plans[3];  // MT = 1, 2, 4
   int tc_S = 0;   // split-K of the tcgen05 path (0 = not planned)
   bool pair = false;  // gate/up pair image (SwiGLU epilogue): physical channels = 2 * N
   int device = 0;
@@ -633,8 +562,8 @@ static int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
-static int make_plan(b2_gemm_wq* h, int mti, bool allow_cluster = true) {
-  Plan& pl = h->plans[mti + (allow_cluster ? 0 : 3)];
+static int make_plan(b2_gemm_wq* h, int mti) {
+  Plan& pl = h->plans[mti];
   if (pl.valid) return B2_OK;
   const int mt = 1 << mti, MP = 8 * mt;
   const bool grouped = h->group_tiles > 0;
@@ -674,23 +603,12 @@ static int make_plan(b2_gemm_wq* h, int mti, bool allow_cluster = true) {
   if (S < 1) S = 1;
   const int force = env_int("B2_GEMM_FORCE_SPLIT", 0);
   if (force > 0) S = force < quanta ? force : quanta;
-  // split-K through a thread-block cluster + DSMEM (<= 16 CTAs, non-portable size allowed) instead of workspace + atomics.
-  // Measured on B200 (Qwen2-7B W4, B=1): 2.39 ms/step with 16-CTA clusters, 2.35 with 8, 2.23 with the workspace path:
-  // gang-scheduling a cluster costs more than the fence/atomic chain it removes, so it is opt-in (B2_GEMM_CLUSTER=N).
-  const int cl_max = env_int("B2_GEMM_CLUSTER", 0);
-  bool cluster = false;
-  if (allow_cluster && cl_max > 1 && S > 1 && force == 0) {
-    if (S > cl_max) S = cl_max;
-    cluster = (size_t)(8 << mti) * kBN * sizeof(float) <= (size_t)nstage * stage_bytes_of(h->d.wbits);  // the ring doubles as reduction scratch
-    if (S > 8) B2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  }
   const int unit_tiles = ((quanta + S - 1) / S) * gt;
   int xt = unit_tiles < xt_cap ? unit_tiles : xt_cap;
   xt = (xt + xq - 1) / xq * xq;
   pl.S = S;
   pl.xt = xt;
   pl.nst_log2 = nst_log2;
-  pl.cluster = cluster;
   pl.smem = smem_for(xt);
   pl.quanta = quanta;
   pl.valid = true;
@@ -847,9 +765,9 @@ size_t b2_gemm_wq_workspace_bytes(b2_gemm_wq_t h, int M) {
   }
   const int mc = M > 32 ? 32 : M;
   const int mti = mt_index_for(mc);
-  if (make_plan(h, mti, false) != B2_OK) return 0;  // sized for the workspace path, which the fused epilogues may take
-  const Plan& pl = h->plans[mti + 3];
-  if (pl.S <= 1 || pl.cluster) return 16;
+  if (make_plan(h, mti) != B2_OK) return 0;
+  const Plan& pl = h->plans[mti];
+  if (pl.S <= 1) return 16;
   return (size_t)h->NG * pl.S * (8 << mti) * kBN * sizeof(float) + 16;
 }
 
@@ -911,10 +829,9 @@ int b2_gemm_wq_run_fused(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, in
   for (int m0 = 0; m0 < M; m0 += 32) {
     const int mc = (M - m0) > 32 ? 32 : (M - m0);
     const int mti = mt_index_for(mc);
-    const bool allow_cluster = !(fuse && fuse->sumsq_out);  // row statistics need the whole tile in one CTA
-    if (int st = make_plan(h, mti, allow_cluster)) return st;
-    const Plan& pl = h->plans[mti + (allow_cluster ? 0 : 3)];
-    if (pl.S > 1 && !pl.cluster && !workspace) return B2_ERR_PARAM;
+    if (int st = make_plan(h, mti)) return st;
+    const Plan& pl = h->plans[mti];
+    if (pl.S > 1 && !workspace) return B2_ERR_PARAM;
     GemmParams p;
     p.packed = (const uint8_t*)h->packed;
     p.sz = h->sz;
@@ -939,9 +856,8 @@ int b2_gemm_wq_run_fused(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, in
     p.norm_inv_hidden = fuse && fuse->norm_hidden > 0 ? 1.0f / (float)fuse->norm_hidden : 0.f;
     p.norm_eps = fuse ? fuse->norm_eps : 0.f;
     p.sumsq_out = fuse ? fuse->sumsq_out : nullptr;
-    p.cluster = pl.cluster ? 1 : 0;
     gemm_kernel_t kern = pick_kernel(h->d.wbits, grouped, 1 << mti);
-    cudaError_t e = launch_cluster(kern, dim3(h->NG * pl.S), dim3(kThreads), (size_t)pl.smem, stream, true, pl.cluster ? pl.S : 1, p);
+    cudaError_t e = launch(kern, dim3(h->NG * pl.S), dim3(kThreads), (size_t)pl.smem, stream, true, p);
     if (e != cudaSuccess) {
       set_last_error("wq_gemm launch", e);
       return B2_ERR_CUDA;
