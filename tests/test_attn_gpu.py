@@ -144,3 +144,36 @@ def test_attention_quantized_long(mode):
     ref = KV.attention_ref(q, kref, vref, lens, nH, 1.0 / np.sqrt(128))
     ok, err = _close(out.float().cpu().numpy().reshape(B, nH, 128), ref)
     assert ok, err
+
+
+def test_attention_i8_ctx_32768():
+    """Maximum size of config C2: one sequence of 32768 tokens, int8 KV spans, Qwen2-7B head geometry —
+    256 spans, every CTA of the persistent grid takes part, partial merge across ~440 pieces per kv-head."""
+    from b200spark import ops
+    nH, nG, span, L = 28, 4, 128, 32768
+    rng = np.random.default_rng(77)
+    cache = ops.SpanCache(1, L, nH, nG, span, KV.QUANT_I8)
+    kref, vref = KV.SpanCacheRef(KV.QUANT_I8, span, nG), KV.SpanCacheRef(KV.QUANT_I8, span, nG)
+    kref.add_sequence(); vref.add_sequence()
+    width = (nH + 2 * nG) * 128
+    q_last = None
+    # the append kernel writes one token per sequence per call: feed it 32768 times (positions on the device)
+    rows = _bf16(rng.standard_normal((L, width)).astype(np.float32))
+    rows_d = rows.cuda()
+    pos = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for t in range(L):
+        q = ops.cache_append(cache, rows_d[t:t + 1], pos)
+        ops.lens_add(pos, 1)
+    x = rows.float().numpy().reshape(L, nH + 2 * nG, 128)
+    for t in range(L):
+        kref.append(0, t, x[t, nH:nH + nG]); vref.append(0, t, x[t, nH + nG:])
+    q_last = x[L - 1, :nH][None]
+    attn = ops.SpanAttn(cache.cfg, 1)
+    ws = ops.Workspace()
+    out = attn(q.reshape(1, -1), cache, torch.tensor([L], dtype=torch.int32, device="cuda"), L, ws)
+    out2 = attn(q.reshape(1, -1), cache, torch.tensor([L], dtype=torch.int32, device="cuda"), L, ws)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+    ref = KV.attention_ref(q_last, kref, vref, [L], nH, 1.0 / np.sqrt(128))
+    ok, err = _close(out.float().cpu().numpy().reshape(1, nH, 128), ref)
+    assert ok, err
