@@ -737,6 +737,13 @@ int b2_gemm_wq_attach_packed(b2_gemm_wq_t h, const void* packed, const void* sca
 }
 
 static int mt_index_for(int M) { return M <= 8 ? 0 : (M <= 16 ? 1 : 2); }
+// rows per launch of the mma.sync kernel.  Sub-channel weights at M > 16 (they have no tcgen05 path yet): the MT=4 grouped
+// variant needs 124 registers (one CTA per SM, 0.05 of HBM at M=32), so they run in passes of 16 rows (MT=2, two CTAs per SM)
+// and stream the weights once per pass.  B2_GEMM_GROUPED_CHUNK=32 restores single-pass MT=4.
+static int rows_per_launch(const b2_gemm_wq* h) {
+  static const int gc = env_int("B2_GEMM_GROUPED_CHUNK", 16);
+  return (h->group_tiles > 0 && gc == 16) ? 16 : 32;
+}
 
 static bool use_tc(const b2_gemm_wq* h, int M) {
   static const int min_m = env_int("B2_GEMM_TC_MIN_M", 17);
@@ -763,7 +770,8 @@ size_t b2_gemm_wq_workspace_bytes(b2_gemm_wq_t h, int M) {
     if (make_tc_plan(h) != B2_OK) return 0;
     return h->tc_S <= 1 ? 16 : (size_t)h->NG * h->tc_S * kTcMaxM * kBN * sizeof(float) + 16;
   }
-  const int mc = M > 32 ? 32 : M;
+  const int rpl = rows_per_launch(h);
+  const int mc = M > rpl ? rpl : M;
   const int mti = mt_index_for(mc);
   if (make_plan(h, mti) != B2_OK) return 0;
   const Plan& pl = h->plans[mti];
@@ -826,8 +834,9 @@ int b2_gemm_wq_run_fused(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, in
     }
     return B2_OK;
   }
-  for (int m0 = 0; m0 < M; m0 += 32) {
-    const int mc = (M - m0) > 32 ? 32 : (M - m0);
+  const int rpl = rows_per_launch(h);
+  for (int m0 = 0; m0 < M; m0 += rpl) {
+    const int mc = (M - m0) > rpl ? rpl : (M - m0);
     const int mti = mt_index_for(mc);
     if (int st = make_plan(h, mti)) return st;
     const Plan& pl = h->plans[mti];

@@ -125,6 +125,7 @@ class DecodeStack:
         self.cfg, self.B, self.max_len = cfg, batch, max_len
         self.tp_rank, self.tp, self.tp_group = tp_rank, tp_size, tp_group
         self.fuse_swiglu = fuse_swiglu
+        self.group_size = group
         self.device = device
         self.n_layers = layers if layers is not None else cfg.layers
         self.kv_mode = KV_MODES[kv]
@@ -271,8 +272,11 @@ class DecodeStack:
             self.next_ids.copy_(torch.gather(self.all_ids, 0, win[None, :])[0])
         ops.lens_add(self.lens_old, 1); n += 1
         ops.lens_add(self.lens_new, 1); n += 1
-        mchunks = (self.B + 63) // 64 if self.B > 16 else 1  # rows per launch: 64 (tcgen05 path) / all (small-M path)
-        n += (mchunks - 1) * ((4 if self.fuse_swiglu else 5) * len(self.layers) + 1)
+        # rows per launch above batch 16: 64 on the tcgen05 path (per-channel int4/int8, bf16 lm_head), 16 for sub-channel
+        # weights (mma.sync path); below, one launch takes the whole batch
+        hchunks = (self.B + 63) // 64 if self.B > 16 else 1
+        qchunks = ((self.B + 15) // 16 if self.group_size != -1 else hchunks) if self.B > 16 else 1
+        n += (qchunks - 1) * (4 if self.fuse_swiglu else 5) * len(self.layers) + (hchunks - 1)
         self.launches_per_step = n
 
     def step(self):
