@@ -1,4 +1,5 @@
-// b200spark — weight-only quantized GEMM for decode batches 17..64 on the 5th-gen tensor cores (tcgen05), sm_100a.
+// b200spark — weight-only quantized (int4 / int8) and dense bf16 GEMM for decode batches 17..64 on the 5th-gen tensor
+// cores (tcgen05), sm_100a.
 //
 // Replaces the reference's "dequantize the whole weight to a [K,N] bf16 workspace, then cuBLAS" fallback
 // (csrc/core/operator/general/gemm_lowp/gemm_a16w4_gpu.cpp:193-210, gemm_a16w8_gpu.cpp:210-237): 4.5 B of HBM
@@ -6,8 +7,8 @@
 //
 //   C^T[128 n x NM m] (fp32, TMEM) += W^T[128 n x 16 k] (bf16, TMEM) * A^T[16 k x NM m] (bf16, shared memory)
 //
-//   warp 0      : TMA producer — int4/int8 weight tiles (same init-time image as the mma.sync kernel) stream
-//                 HBM -> shared memory with cp.async.bulk, ahead of the previous kernel's completion (PDL)
+//   warp 0      : TMA producer — int4/int8/bf16 weight tiles (same init-time image as the mma.sync kernel) stream
+//                 HBM -> shared memory with cp.async.bulk (16 KB stages), ahead of the previous kernel's completion (PDL)
 //   warps 2..5, : dequant — one thread per output channel: LDS.128 -> lop3/shf -> exact bf16 integers (16+q)
 //   warps 9..12   -> tcgen05.st into the A-operand region of TMEM (the dequantized weights never touch shared
 //                 memory: its bandwidth could not carry 2 B/weight at HBM rate).  Two groups of four warps take
@@ -19,8 +20,11 @@
 //   warp 1      : one elected thread issues tcgen05.mma (A from TMEM, B from shared memory, D in TMEM) and
 //                 tcgen05.commit's the pipeline barriers
 //   epilogue    : the dequant warps read D with tcgen05.ld, apply s * (acc - (16+z) * sum a) and park the fp32 tile in
-//                 shared memory; then ALL 416 threads do the split-K partial store / last-CTA reduction and the final
-//                 alpha/bias/activation/residual with 16-byte reads and 8-byte bf16x4 stores.
+//                 the drained activation ring; then ALL 416 threads do the split-K partial store / last-CTA reduction and
+//                 the final alpha/bias/activation/residual (or SwiGLU) with 16-byte reads and 8-byte bf16x4 stores.
+//   persistent  : when there are more (n-group, k-split) units than SMs (gate+up pair, lm_head) one CTA per SM walks
+//                 several units; barriers, TMEM and ring phases carry over and the next unit's first weight stages are
+//                 issued before the epilogue (MULTI instantiation).
 //
 // Roofline: HBM-bound up to M ~ 64 (256 FLOP/B ~ the tensor/HBM ridge); report both.
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
@@ -141,9 +145,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
   uint64_t* bars = reinterpret_cast<uint64_t*>(suma + kTcNM);
   uint64_t* wfull = bars;                 // [NSW] weights landed (TMA tx)
   uint64_t* wfree = wfull + kTcNSW;       // [NSW] dequant warps done with the smem stage (4 arrivals)
-  uint64_t* xfull = wfree + kTcNSW;       // [NSX] activations landed (TMA tx)
+  uint64_t* xfull = wfree + kTcNSW;       // [NSX] (reserved; the activation TMA completes on afull)
   uint64_t* xsum = xfull + kTcNSX;        // [NSX] row sums done with the stage (2 arrivals)
-  uint64_t* afull = xsum + kTcNSX;        // [NAB] dequantized A stage stored in TMEM (4 arrivals)
+  uint64_t* afull = xsum + kTcNSX;        // [NAB] stage ready: activation TMA tx + 4 dequant-warp arrivals (A stage in TMEM)
   uint64_t* mdone = afull + NAB;          // [NSX] tensor core done with stage (tcgen05.commit): frees A buffer + X slot
   uint64_t* dfull = mdone + kTcNSX;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dfull + 1);
@@ -155,7 +159,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
 
   if (tid == 0) {
     for (int i = 0; i < NSW; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wfree[i], 4); }
-    // xfull: TMA tx (sum warps wait on it); ready: TMA tx + 4 dequant-warp arrivals (the MMA thread waits on it)
+    // afull = stage ready: activation TMA tx + 4 dequant-warp arrivals (the MMA thread and the row-sum warps wait on it)
     for (int i = 0; i < kTcNSX; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xsum[i], 2); mbar_init(&mdone[i], 1); mbar_init(&afull[i], 5); }
     mbar_init(dfull, 1);
     fence_mbar_init();
