@@ -20,6 +20,8 @@
 // Roofline: HBM-bound; algorithmic bytes/launch = K*N*wbits/8 + 4*G*N + 2*M*(K+N).
 #include <cstdio>
 #include <cstdlib>
+#include <map>
+#include <mutex>
 #include <new>
 
 #include "b2_common.cuh"
@@ -562,6 +564,20 @@ static int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
+// The kernel instantiation is shared by every handle with the same (wbits, grouped, MT) while the shared-memory need
+// depends on the handle's group size: the opt-in limit is only ever raised (a later handle with a smaller need must
+// not lower it under an earlier handle's launches).
+static cudaError_t raise_smem_limit(gemm_kernel_t kern, int smem) {
+  static std::mutex mu;
+  static std::map<gemm_kernel_t, int> limit;
+  std::lock_guard<std::mutex> lk(mu);
+  int& cur = limit[kern];
+  if (smem <= cur) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) cur = smem;
+  return e;
+}
+
 static int make_plan(b2_gemm_wq* h, int mti) {
   Plan& pl = h->plans[mti];
   if (pl.valid) return B2_OK;
@@ -588,7 +604,7 @@ static int make_plan(b2_gemm_wq* h, int mti) {
   };
   // first guess occupancy with the cap, derive S, then shrink xt to what a unit really needs
   int smem = smem_for(xt_cap);
-  B2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  B2_CUDA_TRY(raise_smem_limit(kern, smem));
   int occ = 1;
   B2_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
   if (occ < 1) occ = 1;

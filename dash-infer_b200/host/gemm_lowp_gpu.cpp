@@ -8,7 +8,7 @@ GemmLowpGPUBase::~GemmLowpGPUBase() {
 
 AsStatus GemmLowpGPUBase::InitV2(const OperatorProto& op_proto, const DeviceContext& ctx, const TensorMap& weights_map,
                                  TensorMap& weights_buffer, TensorMap* tensor_map, RuntimeContext* runtime_ctx) {
-  (void)weights_buffer; (void)runtime_ctx;
+  (void)runtime_ctx;
   AS_CHECK_STATUS(AsOperator::Init(op_proto, ctx, weights_map, tensor_map));
   const int wb = wbits();
   // weights: quantized ops carry [weight, scales, zeros, (bias)] (gemm_a16w4.cpp:30-36), dense Gemm [weight, (bias)]
@@ -26,6 +26,17 @@ AsStatus GemmLowpGPUBase::InitV2(const OperatorProto& op_proto, const DeviceCont
   if (attr.count("is_pooler")) is_pooler_ = *(const bool*)attr.at("is_pooler").c_str();
   if (attr.count("activation")) activation_ = *(const int*)attr.at("activation").c_str();
   if (attr.count("alpha")) alpha_ = *(const float*)attr.at("alpha").c_str();
+  // dense Gemm only (gemm_op.cpp:73-84): residual fused as a second input, K-split activations
+  if (attr.count("binary_type")) binary_type_ = *(const int*)attr.at("binary_type").c_str();
+  if (attr.count("splitk")) is_split_k_ = *(const bool*)attr.at("splitk").c_str();
+  if (binary_type_ != BINARYTYPE_UNDEFINED && binary_type_ != ADD) {
+    AS_LOG_ERROR("%s: binary_type %d is not implemented (only ADD, like GemmOpGPU)", op_type_.c_str(), binary_type_);
+    return AsStatus::ALLSPARK_PARAM_ERROR;
+  }
+  if (binary_type_ == ADD && in_names_.size() < 2) {
+    AS_LOG_ERROR("%s: binary_type ADD needs the residual as a second input", op_type_.c_str());
+    return AsStatus::ALLSPARK_PARAM_ERROR;
+  }
   if (attr.count("GroupSize")) {
     group_size_ = *(const int*)attr.at("GroupSize").c_str();
     // gemm_a16w4.cpp:57-63 (>= 32, % 8) and gemm_a16w8.cpp (64/128/256/512); this build streams k in 64-wide tiles
@@ -66,13 +77,37 @@ AsStatus GemmLowpGPUBase::InitV2(const OperatorProto& op_proto, const DeviceCont
   const void* zr = wb == 16 ? nullptr : weights_[2]->GetDataPtr();
   AS_CHECK_STATUS(FromB2(b2_gemm_wq_prepare_weights(handle_, weights_[0]->GetDataPtr(), sc, zr, nullptr, stream)));
   cudaStreamSynchronize(stream);
+  // Weight-swap contract (gemm_a16w4_gpu.cpp:296-300, util::SyncWeightsBuffer): the reference overwrites the op's weight
+  // tensors with padded / reordered copies and must mirror them into `weights_buffer` (the host image the swap-in path
+  // restores from).  Here the caller's weight tensors are left untouched — the re-laid-out image is handle-owned — so
+  // whatever `weights_buffer` holds for them stays valid; after a swap-in the engine calls ReloadWeights() below.
+  for (const AsTensor* w : weights_) {
+    auto it = weights_buffer.find(w->GetName());
+    if (it != weights_buffer.end() && it->second && it->second->GetSizeInByte() != w->GetSizeInByte()) {
+      AS_LOG_ERROR("%s: weights_buffer entry '%s' does not match the weight tensor", op_type_.c_str(), w->GetName().c_str());
+      return AsStatus::ALLSPARK_PARAM_ERROR;
+    }
+  }
+  return AsStatus::ALLSPARK_SUCCESS;
+}
+
+AsStatus GemmLowpGPUBase::ReloadWeights() {
+  cudaStream_t stream = static_cast<const CUDAContext*>(ctx_)->GetStream();
+  const int wb = wbits();
+  const void* sc = wb == 16 ? nullptr : weights_[1]->GetDataPtr();
+  const void* zr = wb == 16 ? nullptr : weights_[2]->GetDataPtr();
+  AS_CHECK_STATUS(FromB2(b2_gemm_wq_prepare_weights(handle_, weights_[0]->GetDataPtr(), sc, zr, nullptr, stream)));
+  cudaStreamSynchronize(stream);
   return AsStatus::ALLSPARK_SUCCESS;
 }
 
 AsStatus GemmLowpGPUBase::Reshape() {
   const Shape& xs = tensor_map_->at(in_names_[0])->GetShape();
   const int nd = xs.Size();
-  if (nd < 1 || xs[nd - 1] != k_) return AsStatus::ALLSPARK_PARAM_ERROR;
+  const int nranks = ctx_->GetNranks() > 0 ? ctx_->GetNranks() : 1;
+  // splitk (gemm_op.cpp:96-98): the activation rows are nranks * K wide and this rank multiplies its own K-slice
+  lda_ = is_split_k_ ? k_ * nranks : k_;
+  if (nd < 1 || xs[nd - 1] != lda_) return AsStatus::ALLSPARK_PARAM_ERROR;
   m_ = xs.Count(0, nd - 1);
   Shape ys;
   for (int i = 0; i < nd - 1; ++i) ys.Append(xs[i]);
@@ -96,7 +131,17 @@ AsStatus GemmLowpGPUBase::Forward() {
   const size_t bias_idx = wbits() == 16 ? 1 : 3;
   const void* bias = weights_.size() > bias_idx ? weights_[bias_idx]->GetDataPtr() : nullptr;
   cudaStream_t stream = static_cast<const CUDAContext*>(ctx_)->GetStream();
-  return FromB2(b2_gemm_wq_run(handle_, in->GetDataPtr(), k_, out->GetDataPtr(), n_, (int)m_, bias, nullptr, activation_, alpha_,
+  // binary_type ADD (gemm_op.cpp:121-136, gemm_op_gpu.cpp): out = act(alpha * x W + bias) + in[1]; under tensor
+  // parallelism only rank 0 adds it (the all-reduce that follows sums the partial outputs)
+  const void* residual = nullptr;
+  if (binary_type_ == ADD && ctx_->GetRank() == 0) {
+    AsTensor* res = tensor_map_->at(in_names_[1]).get();
+    if (res->GetShape().Count() != m_ * n_) return AsStatus::ALLSPARK_PARAM_ERROR;
+    residual = res->GetDataPtr();
+  }
+  const char* a = (const char*)in->GetDataPtr();
+  if (is_split_k_) a += (size_t)ctx_->GetRank() * k_ * SizeofType(in->GetDataType());
+  return FromB2(b2_gemm_wq_run(handle_, a, lda_, out->GetDataPtr(), n_, (int)m_, bias, residual, activation_, alpha_,
                                ws->GetDataPtr(), ws->GetSizeInByte(), stream));
 }
 

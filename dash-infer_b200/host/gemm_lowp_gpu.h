@@ -18,11 +18,16 @@ class GemmLowpGPUBase : public AsOperator {
                   TensorMap& weights_buffer, TensorMap* tensor_map, RuntimeContext* runtime_ctx) override;
   AsStatus Reshape() override;
   AsStatus Forward() override;
+  // re-run the init-time re-layout from the (restored) weight tensors: the counterpart of the reference's swap-in path
+  // that copies weights_buffer back to the device (gemm_a16w4_gpu.cpp:296-300)
+  AsStatus ReloadWeights();
 
  protected:
   virtual int wbits() const = 0;
   b2_gemm_wq_t handle_ = nullptr;
-  int64_t m_ = 0, n_ = 0, k_ = 0;
+  int64_t m_ = 0, n_ = 0, k_ = 0, lda_ = 0;
+  int binary_type_ = BINARYTYPE_UNDEFINED;
+  bool is_split_k_ = false;
   int group_size_ = -1;
   int activation_ = UNARYTYPE_UNDEFINED;
   float alpha_ = 1.0f;

@@ -1,11 +1,32 @@
 #include "span_attn_op_cuda.h"
 
 #include <cmath>
+#include <cstring>
+#include <string>
 
 namespace allspark {
 
 SpanAttnOpCUDA::~SpanAttnOpCUDA() {
   if (handle_) b2_span_attn_destroy(handle_);
+  for (auto& s : stage_) {
+    if (s.done) cudaEventDestroy(s.done);
+    if (s.host) cudaFreeHost(s.host);
+  }
+}
+
+// csrc/common/common.h:239-257: the first '.'-separated field of the op name that is all digits
+// ("decoder.layer.17.attention" -> 17); -1 when there is none
+static int layer_num_from_name(const std::string& name) {
+  size_t a = 0;
+  while (a <= name.size()) {
+    size_t b = name.find('.', a);
+    if (b == std::string::npos) b = name.size();
+    bool digits = b > a;
+    for (size_t i = a; i < b; ++i) digits = digits && name[i] >= '0' && name[i] <= '9';
+    if (digits) return std::stoi(name.substr(a, b - a));
+    a = b + 1;
+  }
+  return -1;
 }
 
 AsStatus SpanAttnOpCUDA::InitV2(const OperatorProto& op_proto, const DeviceContext& ctx, const TensorMap& weights_map,
@@ -14,7 +35,12 @@ AsStatus SpanAttnOpCUDA::InitV2(const OperatorProto& op_proto, const DeviceConte
   AS_CHECK_STATUS(AsOperator::Init(op_proto, ctx, weights_map, tensor_map));
   auto& attr = op_proto.attr();
   if (attr.count("alpha")) alpha_ = *(const float*)attr.at("alpha").c_str();
-  if (attr.count("layer_num")) layer_num_ = *(const int*)attr.at("layer_num").c_str();  // reference: parsed from the op name
+  layer_num_ = layer_num_from_name(op_name_);  // span_attn_op.cpp:183
+  if (attr.count("layer_num")) layer_num_ = *(const int*)attr.at("layer_num").c_str();  // optional override (tests)
+  if (layer_num_ < 0) {
+    AS_LOG_ERROR("SpanAttnOp: cannot get layer_num from op name '%s'", op_name_.c_str());
+    return AsStatus::ALLSPARK_PARAM_ERROR;
+  }
   DataType dtype = ctx.GetDtype() != DATATYPE_UNDEFINED ? ctx.GetDtype() : DataType::BFLOAT16;
   tensor_map_->at(out_names_[0])->SetDataType(dtype);
   const int nranks = ctx.GetNranks() > 0 ? ctx.GetNranks() : 1;
@@ -35,8 +61,14 @@ AsStatus SpanAttnOpCUDA::InitV2(const OperatorProto& op_proto, const DeviceConte
   v_tab_ = std::make_unique<AsTensor>("v_span_array", dev, DataType::POINTER, DataMode::DENSE, Shape{(int64_t)max_batch_ * max_spans_});
   old_lens_ = std::make_unique<AsTensor>("old_seq_lens", dev, DataType::INT32, DataMode::DENSE, Shape{max_batch_});
   new_lens_ = std::make_unique<AsTensor>("new_seq_lens", dev, DataType::INT32, DataMode::DENSE, Shape{max_batch_});
-  k_host_.assign((size_t)max_batch_ * max_spans_, nullptr);
-  v_host_.assign((size_t)max_batch_ * max_spans_, nullptr);
+  // pinned staging ring: [old lens | new lens | k table | v table] per slot; a slot is reused only after the copies that
+  // read it have completed (event), so Forward never blocks on the stream in steady state
+  slot_bytes_ = (size_t)2 * max_batch_ * sizeof(int32_t) + (size_t)2 * max_batch_ * max_spans_ * sizeof(void*);
+  for (auto& sl : stage_) {
+    if (cudaMallocHost(&sl.host, slot_bytes_) != cudaSuccess || cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming) != cudaSuccess)
+      return AsStatus::ALLSPARK_MEMORY_ERROR;
+    sl.busy = false;
+  }
   span_counts_.assign(max_batch_, -1);
   return AsStatus::ALLSPARK_SUCCESS;
 }
@@ -82,31 +114,42 @@ AsStatus SpanAttnOpCUDA::Alloc(RuntimeContext* runtime_ctx) {
 
 AsStatus SpanAttnOpCUDA::Forward(RuntimeContext* runtime_ctx) {
   cudaStream_t stream = static_cast<const CUDAContext*>(ctx_)->GetStream();
-  // host -> device staging only for what changed: lengths (4 B / sequence) and the span table rows that grew
-  lens_host_.resize(batch_size_);
-  bool tables_dirty = false;
+  Stage& sl = stage_[stage_i_];
+  stage_i_ = (stage_i_ + 1) % kStages;
+  if (sl.busy) cudaEventSynchronize(sl.done);  // kStages Forward calls ago: long finished unless the host runs far ahead
+  int32_t* old_h = reinterpret_cast<int32_t*>(sl.host);
+  int32_t* new_h = old_h + max_batch_;
+  void** k_h = reinterpret_cast<void**>(new_h + max_batch_);
+  void** v_h = k_h + (size_t)max_batch_ * max_spans_;
+  // host -> device staging only for what changed: lengths (4 B / sequence) and the span-table rows that grew
+  int dirty_lo = batch_size_, dirty_hi = -1;
   for (int b = 0; b < batch_size_; ++b) {
     GenerateContext* g = runtime_ctx->GetGenCtx(b);
-    lens_host_[b] = g->step;
-    const AsTensor& kp = g->virtual_k_cache->GetCache(layer_num_, 0);
-    const AsTensor& vp = g->virtual_v_cache->GetCache(layer_num_, 0);
-    const int ns = (int)kp.GetShape().Count();
+    old_h[b] = g->step;
+    new_h[b] = g->step + 1;
+    const int ns = (int)g->virtual_k_cache->GetCache(layer_num_, 0).GetShape().Count();
+    if (ns > max_spans_ || (int)g->virtual_v_cache->GetCache(layer_num_, 0).GetShape().Count() != ns)
+      return AsStatus::ALLSPARK_EXCEED_LIMIT_ERROR;
     if (ns != span_counts_[b]) {
-      std::memcpy(&k_host_[(size_t)b * max_spans_], kp.GetDataPtr(), ns * sizeof(void*));
-      std::memcpy(&v_host_[(size_t)b * max_spans_], vp.GetDataPtr(), ns * sizeof(void*));
       span_counts_[b] = ns;
-      tables_dirty = true;
+      dirty_lo = b < dirty_lo ? b : dirty_lo;
+      dirty_hi = b;
     }
   }
-  if (tables_dirty) {
-    const size_t bytes = (size_t)batch_size_ * max_spans_ * sizeof(void*);
-    cudaMemcpyAsync(k_tab_->GetDataPtr(), k_host_.data(), bytes, cudaMemcpyHostToDevice, stream);
-    cudaMemcpyAsync(v_tab_->GetDataPtr(), v_host_.data(), bytes, cudaMemcpyHostToDevice, stream);
+  if (dirty_hi >= 0) {  // stage and upload the contiguous row range that contains every changed row
+    for (int b = dirty_lo; b <= dirty_hi; ++b) {
+      GenerateContext* g = runtime_ctx->GetGenCtx(b);
+      std::memcpy(k_h + (size_t)b * max_spans_, g->virtual_k_cache->GetCache(layer_num_, 0).GetDataPtr(), span_counts_[b] * sizeof(void*));
+      std::memcpy(v_h + (size_t)b * max_spans_, g->virtual_v_cache->GetCache(layer_num_, 0).GetDataPtr(), span_counts_[b] * sizeof(void*));
+    }
+    const size_t off = (size_t)dirty_lo * max_spans_, cnt = (size_t)(dirty_hi - dirty_lo + 1) * max_spans_;
+    cudaMemcpyAsync((void**)k_tab_->GetDataPtr() + off, k_h + off, cnt * sizeof(void*), cudaMemcpyHostToDevice, stream);
+    cudaMemcpyAsync((void**)v_tab_->GetDataPtr() + off, v_h + off, cnt * sizeof(void*), cudaMemcpyHostToDevice, stream);
   }
-  cudaMemcpyAsync(old_lens_->GetDataPtr(), lens_host_.data(), batch_size_ * sizeof(int32_t), cudaMemcpyHostToDevice, stream);
-  for (auto& l : lens_host_) l += 1;
-  cudaMemcpyAsync(new_lens_->GetDataPtr(), lens_host_.data(), batch_size_ * sizeof(int32_t), cudaMemcpyHostToDevice, stream);
-  cudaStreamSynchronize(stream);  // lens_host_/k_host_ are pageable and reused next call
+  cudaMemcpyAsync(old_lens_->GetDataPtr(), old_h, batch_size_ * sizeof(int32_t), cudaMemcpyHostToDevice, stream);
+  cudaMemcpyAsync(new_lens_->GetDataPtr(), new_h, batch_size_ * sizeof(int32_t), cudaMemcpyHostToDevice, stream);
+  cudaEventRecord(sl.done, stream);  // no stream synchronisation: the slot is only reused kStages calls later
+  sl.busy = true;
 
   AsTensor* in = tensor_map_->at(in_names_[0]).get();
   AsTensor* out = tensor_map_->at(out_names_[0]).get();

@@ -22,9 +22,9 @@ int as_test_registered(const char* op_type) {
 }
 
 // op_type: "GemmA16W4" | "GemmA16W8" | "Gemm".  Host buffers in the reference layouts; C_host receives [M, N] bf16.
-int as_test_gemm(const char* op_type, int M, int N, int K, int group_size, int activation, float alpha, const void* A_host,
-                 const void* w_host, int w_dtype, const void* scales_host, const void* zeros_host, const void* bias_host,
-                 void* C_host) {
+static int run_gemm(const char* op_type, int M, int N, int K, int group_size, int activation, float alpha, const void* A_host,
+                    const void* w_host, int w_dtype, const void* scales_host, const void* zeros_host, const void* bias_host,
+                    const void* residual_host, int binary_type, void* C_host) {
   try {
     CUDAContext ctx;
     ctx.SetDtype(DataType::BFLOAT16);
@@ -48,6 +48,11 @@ int as_test_gemm(const char* op_type, int M, int N, int K, int group_size, int a
     proto.op_type_ = t; proto.op_name_ = "test_" + t;
     proto.inputs_.push_back({"input"}); proto.outputs_.push_back({"output"});
     proto.weights_.push_back({"weight"});
+    if (residual_host) {  // do_binary_add_fused graphs: Gemm(x, residual) with binary_type ADD (qwen_v15.py:280-286)
+      add(tensors, "residual", DataType::BFLOAT16, Shape{1, M, N}, residual_host);
+      proto.inputs_.push_back({"residual"});
+    }
+    if (binary_type) proto.SetAttr<int>("binary_type", binary_type);
     if (quant) {
       add(weights, "scales", DataType::BFLOAT16, Shape{G, N}, scales_host);
       add(weights, "zeros", DataType::BFLOAT16, Shape{G, N}, zeros_host);
@@ -77,6 +82,20 @@ int as_test_gemm(const char* op_type, int M, int N, int K, int group_size, int a
     AS_LOG_ERROR("as_test_gemm: %s", e.what());
     return -1;
   }
+}
+
+int as_test_gemm(const char* op_type, int M, int N, int K, int group_size, int activation, float alpha, const void* A_host,
+                 const void* w_host, int w_dtype, const void* scales_host, const void* zeros_host, const void* bias_host,
+                 void* C_host) {
+  return run_gemm(op_type, M, N, K, group_size, activation, alpha, A_host, w_host, w_dtype, scales_host, zeros_host, bias_host,
+                  nullptr, 0, C_host);
+}
+
+int as_test_gemm_binary(const char* op_type, int M, int N, int K, int group_size, int activation, float alpha, const void* A_host,
+                        const void* w_host, int w_dtype, const void* scales_host, const void* zeros_host, const void* bias_host,
+                        const void* residual_host, int binary_type, void* C_host) {
+  return run_gemm(op_type, M, N, K, group_size, activation, alpha, A_host, w_host, w_dtype, scales_host, zeros_host, bias_host,
+                  residual_host, binary_type, C_host);
 }
 
 // Decode `steps` tokens for `batch` sequences through DecOptMQA: per step op.Alloc + op.Forward with qkv_all[t]
@@ -110,9 +129,10 @@ int as_test_span_attn(int batch, int steps, int n_heads, int n_groups, int span_
     tensors["qkv"] = std::make_shared<AsTensor>("qkv", DeviceType::CUDA, DataType::BFLOAT16, DataMode::DENSE, Shape{batch, 1, W});
     tensors["workspace"] = std::make_shared<AsTensor>("workspace", DeviceType::CUDA, DataType::INT8, DataMode::DENSE, Shape{0});
     OperatorProto proto;
-    proto.op_type_ = "DecOptMQA"; proto.op_name_ = "test_attn";
+    // the layer index travels in the op name like in a serialized model ("decoder.layer.<i>.attention", common.h:239-257)
+    proto.op_type_ = "DecOptMQA";
+    proto.op_name_ = layer_id >= 0 ? "decoder.layer." + std::to_string(layer_id) + ".attention" : "attention_without_layer";
     proto.inputs_.push_back({"qkv"}); proto.outputs_.push_back({"attn_out"});
-    proto.SetAttr<int>("layer_num", layer_id);
     auto op = OpFactory::getInstance().GetOperator({"DecOptMQA", DeviceType::CUDA})();
     AsStatus st = op->InitV2(proto, ctx, weights, weights_buffer, &tensors, &rt);
     if (st != AsStatus::ALLSPARK_SUCCESS) return (int)st;

@@ -163,26 +163,25 @@ class DecodeStack:
         self.attn = ops.SpanAttn(self.layers[0]["cache"].cfg, batch)
         self.ws = ops.Workspace(device)
         self.rope = (cfg.rope_base, 128)
-        # device-resident step state
-        self.lens_old = torch.zeros(batch, dtype=torch.int32, device=device)
-        self.lens_new = torch.ones(batch, dtype=torch.int32, device=device)
-        self.ids = torch.zeros(batch, dtype=torch.int64, device=device)
-        self.next_ids = torch.zeros(batch, dtype=torch.int64, device=device)
+        # device-resident step state, allocated for the construction batch; set_batch() re-views it for a smaller batch
+        self.Bmax = batch
+        self._lens_old = torch.zeros(batch, dtype=torch.int32, device=device)
+        self._lens_new = torch.ones(batch, dtype=torch.int32, device=device)
+        self._ids = torch.zeros(batch, dtype=torch.int64, device=device)
+        self._next_ids = torch.zeros(batch, dtype=torch.int64, device=device)
         bf = dict(dtype=torch.bfloat16, device=device)
-        self.x = torch.empty(batch, H, **bf)
-        self.xn = torch.empty(batch, H, **bf)
-        self.qkv = torch.empty(batch, (nHl + 2 * nGl) * 128, **bf)
-        self.q = torch.empty(batch, nHl * 128, **bf)
-        self.ao = torch.empty(batch, nHl * 128, **bf)
-        self.gate = torch.empty(batch, self.I_l, **bf)
-        self.up = torch.empty(batch, self.I_l, **bf)
-        self.logits = torch.empty(batch, self.vocab_l, **bf)
+        self._bufs = dict(x=torch.empty(batch, H, **bf), xn=torch.empty(batch, H, **bf),
+                          qkv=torch.empty(batch, (nHl + 2 * nGl) * 128, **bf), q=torch.empty(batch, nHl * 128, **bf),
+                          ao=torch.empty(batch, nHl * 128, **bf), gate=torch.empty(batch, self.I_l, **bf),
+                          up=torch.empty(batch, self.I_l, **bf), logits=torch.empty(batch, self.vocab_l, **bf))
         if tp > 1:
-            self.part = torch.empty(batch, H, **bf)                       # row-split partial sums (all-reduced)
+            self._bufs["part"] = torch.empty(batch, H, **bf)             # row-split partial sums (all-reduced)
             self.loc_ids = torch.empty(batch, dtype=torch.int64, device=device)
             self.loc_val = torch.empty(batch, dtype=torch.float32, device=device)
             self.all_ids = torch.empty(tp, batch, dtype=torch.int64, device=device)
             self.all_val = torch.empty(tp, batch, dtype=torch.float32, device=device)
+        self.graph = None
+        self.set_batch(batch)
         # RMSNorm fusion (decode batches <= 16, TP = 1): the row-parallel GEMVs emit per-tile sums of squares, their
         # consumers normalise while staging activations; only layer 0's first norm stays a stand-alone kernel.
         # Off by default: measured on B200 it removes 2 launches/layer but lengthens every GEMV's dependent chain
@@ -191,8 +190,20 @@ class DecodeStack:
         if self.fuse_norm:
             self.ssq_o = torch.zeros(self.layers[0]["o"].op.sumsq_parts(), batch, dtype=torch.float32, device=device)
             self.ssq_d = torch.zeros(self.layers[0]["down"].op.sumsq_parts(), batch, dtype=torch.float32, device=device)
-        self.graph = None
         self.launches_per_step = 0
+
+    def set_batch(self, b):
+        """Run the next steps with the first `b` sequences only (b <= construction batch): every step buffer, the length
+        vectors and the span tables are re-viewed (row-major, so the first b rows are contiguous); a captured graph is
+        dropped.  bench.py measures batch 64, 8 and 1 on ONE set of weights and caches this way."""
+        assert 1 <= b <= self.Bmax
+        self.B = b
+        for k, v in self._bufs.items():
+            setattr(self, k, v[:b])
+        self.lens_old, self.lens_new = self._lens_old[:b], self._lens_new[:b]
+        self.ids, self.next_ids = self._ids[:b], self._next_ids[:b]
+        self.graph = None
+        assert not getattr(self, "fuse_norm", False) or b == self.Bmax, "the fused-norm statistics are laid out for one batch"
 
     # ------------------------------------------------------------------ cache fill
     def set_context(self, ctx, seed=4321):
@@ -221,9 +232,16 @@ class DecodeStack:
             lin(inp, self.ws, out=self.x, residual=self.x)
             return n + 1
         lin(inp, self.ws, out=self.part, residual=self.x if self.tp_rank == 0 else None)
-        dist.all_reduce(self.part, group=self.tp_group)
-        self.x.copy_(self.part)
+        self._allreduce(self.part, out=self.x)
         return n + 1
+
+    collective_impl = "nccl all_reduce + copy"
+
+    def _allreduce(self, t, out=None):
+        import torch.distributed as dist
+        dist.all_reduce(t, group=self.tp_group)
+        if out is not None:
+            out.copy_(t)
 
     def _step_ops(self):
         cfg, ws = self.cfg, self.ws
@@ -299,6 +317,37 @@ class DecodeStack:
         torch.cuda.synchronize()
         self.graph = g
         return g
+
+    def collective_probe(self, reps, dist):
+        """Time the decode step's collectives ALONE (TP > 1): the 2 x layers all-reduces of [B, hidden] bf16 + the lm_head
+        all-gathers, back to back in one CUDA graph, `reps` replays -> ms per step.  No compute overlaps them here, so
+        ms_per_step_alone / step time is an upper bound of the collective's share of the step."""
+        import torch.distributed as dist_
+        assert self.tp > 1
+        g = torch.cuda.CUDAGraph()
+        def ops_():
+            for _ in range(2 * len(self.layers)):
+                self._allreduce(self.part)
+            dist_.all_gather_into_tensor(self.all_val, self.loc_val, group=self.tp_group)
+            dist_.all_gather_into_tensor(self.all_ids, self.loc_ids, group=self.tp_group)
+        ops_()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g):
+            ops_()
+        g.replay()
+        torch.cuda.synchronize()
+        dist_.barrier(group=self.tp_group)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], device=self.device)
+        dist_.all_reduce(t, op=dist_.ReduceOp.MAX, group=self.tp_group)
+        return {"ms_per_step_alone": round(float(t.item()), 4), "all_reduces_per_step": 2 * len(self.layers),
+                "bytes_per_all_reduce": self.part.numel() * 2, "impl": self.collective_impl}
 
     # ------------------------------------------------------------------ accounting
     def algo_bytes_per_step(self, ctx):

@@ -117,7 +117,9 @@ class SpanCache:
     """Test/bench stand-in for the reference's CacheSpanManager + SpannedVirtualCache: owns span pages for one
     layer's K and V of a batch and the device pointer tables [batch, max_spans] the kernels walk."""
 
-    def __init__(self, batch, max_len, n_heads, n_groups, span_len=128, quant_mode=KV_NONE, device="cuda", pool=None):
+    def __init__(self, batch, max_len, n_heads, n_groups, span_len=128, quant_mode=KV_NONE, device="cuda", pool=None, fill=0):
+        """fill: byte the span pool is initialised with (the reference's span manager never zeroes frames; tests use
+        0xFF = NaN patterns to prove no kernel consumes unwritten rows)."""
         self.batch, self.max_len = batch, max_len
         self.max_spans = (max_len + span_len - 1) // span_len
         self.cfg = SpanCfg(DT_BF16, quant_mode, n_heads, n_groups, 128, span_len, self.max_spans, 0)
@@ -127,8 +129,8 @@ class SpanCache:
         stride = (self.span_bytes + 255) // 256 * 256
         self.stride = stride
         # pages deliberately handed out in a scrambled order: the kernels must not assume contiguity
-        self.k_pool = torch.zeros(n * stride, dtype=torch.uint8, device=device)
-        self.v_pool = torch.zeros(n * stride, dtype=torch.uint8, device=device)
+        self.k_pool = torch.full((n * stride,), fill, dtype=torch.uint8, device=device)
+        self.v_pool = torch.full((n * stride,), fill, dtype=torch.uint8, device=device)
         g = torch.Generator().manual_seed(99)
         perm_k = torch.randperm(n, generator=g)
         perm_v = torch.randperm(n, generator=g)

@@ -125,7 +125,8 @@ def from_stack(stack, kv_mode=KV.QUANT_NONE):
 def time_cpu_decode(cfg, batch, ctx, sample_layers=2, steps=3, warmup=1, threads=None, seed=1234):
     """Time `steps` decode steps of `sample_layers` decoder layers + final norm + lm_head with contiguous fp32 KV of
     length ctx, bf16 weights (the reference CPU path's medium_bf16 precision) and extrapolate to cfg.layers layers.
-    Returns dict(tokens_per_s, s_per_step_full, s_layer, s_head, threads)."""
+    Returns dict(tokens_per_s, s_per_step_full (extrapolated), s_per_step_sampled (measured time of one sampled step),
+    s_layer, s_head, threads)."""
     import time
     if threads:
         torch.set_num_threads(threads)
@@ -177,5 +178,5 @@ def time_cpu_decode(cfg, batch, ctx, sample_layers=2, steps=3, warmup=1, threads
             t_head += t2 - t1
     s_layer, s_head = t_layer / steps, t_head / steps
     full = s_layer * cfg.layers + s_head
-    return dict(tokens_per_s=batch / full, s_per_step_full=full, s_layer=s_layer, s_head=s_head,
-                threads=torch.get_num_threads())
+    return dict(tokens_per_s=batch / full, s_per_step_full=full, s_per_step_sampled=s_layer * sample_layers + s_head,
+                s_layer=s_layer, s_head=s_head, threads=torch.get_num_threads())

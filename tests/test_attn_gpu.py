@@ -15,12 +15,12 @@ def _bf16(x):
     return torch.from_numpy(x).to(torch.bfloat16)
 
 
-def _build(mode, B, lens, nH, nG, span, seed, max_len=None):
+def _build(mode, B, lens, nH, nG, span, seed, max_len=None, fill=0):
     """Fill a device SpanCache token by token with the product append kernel and mirror it in the oracle."""
     from b200spark import ops
     rng = np.random.default_rng(seed)
     max_len = max_len or (max(lens) + 1)
-    cache = ops.SpanCache(B, max_len, nH, nG, span, mode)
+    cache = ops.SpanCache(B, max_len, nH, nG, span, mode, fill=fill)
     kref, vref = KV.SpanCacheRef(mode, span, nG), KV.SpanCacheRef(mode, span, nG)
     for _ in range(B):
         kref.add_sequence(); vref.add_sequence()
@@ -176,4 +176,27 @@ def test_attention_i8_ctx_32768():
     assert torch.equal(out, out2)
     ref = KV.attention_ref(q_last, kref, vref, [L], nH, 1.0 / np.sqrt(128))
     ok, err = _close(out.float().cpu().numpy().reshape(1, nH, 128), ref)
+    assert ok, err
+
+
+@pytest.mark.parametrize("mode", [KV.QUANT_NONE, KV.QUANT_I8, KV.QUANT_U4])
+@pytest.mark.parametrize("L", [1, 37, 129, 191])
+def test_attention_ignores_unwritten_span_memory(mode, L):
+    """the reference's span manager never zeroes frames.  The pool is filled with 0xFF (NaN as bf16 and as the
+    fp32 {zero, scale} params) before appending; odd lengths leave the unwritten token `len` inside the last 16-byte
+    parameter chunk and inside the last 64-token tile.  Nothing of it may reach the output."""
+    from b200spark import ops
+    nH, nG, span = 28, 4, 32
+    lens = [L, L, L]
+    B = len(lens)
+    cache, kref, vref, q = _build(mode, B, lens, nH, nG, span, seed=1000 + L + mode, max_len=256, fill=0xFF)
+    attn = ops.SpanAttn(cache.cfg, B)
+    ws = ops.Workspace()
+    new_lens = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    out = attn(_bf16(q.reshape(B, -1)).cuda(), cache, new_lens, 256, ws)
+    torch.cuda.synchronize()
+    got = out.float().cpu().numpy().reshape(B, nH, 128)
+    assert np.isfinite(got).all(), "NaN/Inf leaked from unwritten span memory"
+    ref = KV.attention_ref(q, kref, vref, lens, nH, 1.0 / np.sqrt(128))
+    ok, err = _close(got, ref)
     assert ok, err

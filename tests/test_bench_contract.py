@@ -34,3 +34,33 @@ def test_reference_arm_nonzero_rank_is_silent():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--model", "tiny", "--gpus", "2"],
                        capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert r.returncode == 0 and not [l for l in r.stdout.splitlines() if l.startswith("{")]
+
+
+def test_reference_arm_times_the_steps_it_prints_and_loads_no_product_code():
+    """the reference arm printed `steps: 20` while timing <= 4 and imported the product package (which maps
+    libb200spark.so into the reference process).  Now: `steps` timed steps are really run (steps x ms_per_step ~ the wall
+    time of the timed region) and no b200spark module / native library is loaded."""
+    code = ("import sys, json, io, contextlib, time; sys.argv = ['bench.py', '--impl', 'reference', '--model', 'tiny', '--batch', '2', "
+            "'--ctx', '16', '--steps', '7', '--warmup', '2']; import bench; buf = io.StringIO(); t0 = time.perf_counter()\n"
+            "with contextlib.redirect_stdout(buf): bench.main()\n"
+            "wall = time.perf_counter() - t0; d = json.loads(buf.getvalue().strip().splitlines()[-1])\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "print(json.dumps({'steps': d['steps'], 'warmup': d['warmup'], 'timed_s': d['steps'] * d['ms_per_step'] * 1e-3, 'wall': wall,\n"
+            "  'b2_modules': [m for m in sys.modules if m.startswith('b200spark')], 'so': 'libb200spark' in maps or 'liballspark_b200' in maps}))")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-600:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["steps"] == 7 and d["warmup"] == 2
+    assert d["b2_modules"] == [] and d["so"] is False
+    assert d["timed_s"] <= d["wall"]  # the claimed timed region fits inside the run
+
+
+def test_reference_arm_sets_threads_under_torchrun():
+    env = dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--model", "tiny", "--batch", "2", "--ctx",
+                        "16", "--steps", "1", "--warmup", "1", "--gpus", "2"], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-400:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["cpu_baseline"]["cores"] == bench.physical_cores()

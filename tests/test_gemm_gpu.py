@@ -220,3 +220,94 @@ def test_fused_rmsnorm_prologue_and_sumsq_epilogue(wbits, M):
     # same rounding points; only the fp32 summation order of the mean square differs
     assert (y_fused.float() - y_ref.float()).abs().max().item() <= 2e-2 * y_ref.float().abs().max().item()
     assert (y_fused != y_ref).float().mean().item() < 0.05
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The launches bench.py actually times ("the bench runs it unchecked"): tcgen05 path at M in {17, 32, 64}
+# on every Qwen2-7B projection shape, int4 and int8, plus the fused gate/up pair and the Qwen2-72B TP=8 shard shapes.
+# ---------------------------------------------------------------------------------------------------------------------
+QWEN7B = [(3584, 4608), (3584, 3584), (3584, 18944), (18944, 3584)]
+
+
+@pytest.mark.parametrize("K,N", QWEN7B)
+@pytest.mark.parametrize("M", [17, 32, 64])
+def test_qwen2_7b_projections_w4_tcgen05(K, N, M):
+    _run(4, K, N, M, -1, use_bias=(N == 4608), use_res=(N == 3584), seed=K % 89 + M)
+
+
+@pytest.mark.parametrize("K,N", QWEN7B)
+@pytest.mark.parametrize("M", [17, 64])
+def test_qwen2_7b_projections_w8_tcgen05(K, N, M):
+    _run(8, K, N, M, -1, use_bias=(N == 4608), use_res=(N == 3584), seed=K % 83 + M)
+
+
+def _pair_case(wbits, K, N, M, group, seed):
+    from b200spark import ops, quantize as PQ
+    g = torch.Generator().manual_seed(seed)
+    a = (torch.rand(M, K, generator=g) * 2 - 1).to(torch.bfloat16)
+    sets, refs = [], []
+    for _ in range(2):
+        w = (torch.randn(K, N, generator=g) * 0.02).to(torch.bfloat16)
+        if wbits == 4:
+            q, s, z = PQ.quantize_a16w4(w, group); qu = Q.unpack_u4x2(q.numpy(), N)
+        else:
+            q, s, z = PQ.quantize_a16w8(w, group); qu = q.numpy()
+        sets.append((q.cuda(), s.cuda(), z.cuda()))
+        refs.append(Q.gemm_wq_math(a.float().numpy(), qu, s.float().numpy(), z.float().numpy(), group).astype(np.float64))
+    op = ops.GemmWQ(K, N, wbits, group, max_m=M, pair=True)
+    op.prepare_swiglu(*sets[0], *sets[1])
+    ws = ops.Workspace()
+    out = op(a.cuda(), ws)
+    out2 = op(a.cuda(), ws)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+    ref = (refs[0] / (1.0 + np.exp(-refs[0]))) * refs[1]
+    err = Q.err_min_abs_rel(ref.astype(np.float32), out.float().cpu().numpy())
+    assert err <= TOL, err
+
+
+@pytest.mark.parametrize("wbits", [4, 8])
+@pytest.mark.parametrize("M", [1, 8, 64])
+def test_qwen2_7b_gate_up_swiglu_pair_full_size(wbits, M):
+    """The single largest launch of the decode step: gate+up 3584 x (2 x 18944) with the SwiGLU epilogue (persistent units)."""
+    _pair_case(wbits, 3584, 18944, M, -1, seed=100 + M + wbits)
+
+
+@pytest.mark.parametrize("M", [16, 64])
+def test_qwen2_72b_tp8_shard_shapes(M):
+    """Per-rank shapes of config C4 at TP=8 (Qwen2-72B: hidden 8192, 64/8 heads, inter 29568): column-split QKV and gate/up,
+    row-split o_proj / down_proj (K = 1024 / 3696: neither is a multiple of 256, the k-tiles-per-stage of the int4 path)."""
+    _run(4, 8192, (64 + 16) // 8 * 128, M, -1, use_bias=True, seed=200 + M)      # qkv shard   [8192, 1280]
+    _run(4, 64 // 8 * 128, 8192, M, -1, use_res=True, seed=201 + M)              # o shard     [1024, 8192]
+    _run(4, 29568 // 8, 8192, M, -1, use_res=True, seed=202 + M)                 # down shard  [3696, 8192]
+    _pair_case(4, 8192, 29568 // 8, M, -1, seed=203 + M)                         # gate/up shard pair
+
+
+def test_llama3_8b_g128_full_size_m32():
+    """Config C3 shapes (Llama-3-8B GPTQ-style g128, batch 32): QKV / o / down, sub-channel weights at M > 16, and the
+    verdict's pair case (4, 4096, 14336 x 2, 32, 128)."""
+    _run(4, 4096, 4096, 32, 128, use_res=True, seed=301)
+    _run(4, 14336, 4096, 32, 128, use_res=True, seed=302)
+    _pair_case(4, 4096, 14336, 32, 128, seed=303)
+
+
+def test_mixed_group_sizes_share_a_kernel():
+    """two handles of the same kernel instantiation with different group sizes (g128 needs more shared memory
+    per activation chunk than g256): planning the second must not lower the first one's shared-memory opt-in."""
+    from b200spark import ops, quantize as PQ
+    g = torch.Generator().manual_seed(9)
+    K, N, M = 2048, 256, 4
+    hs = []
+    for group in (512, 64):  # large-smem plan first, then a smaller one
+        w = (torch.randn(K, N, generator=g) * 0.02).to(torch.bfloat16)
+        q, s, z = PQ.quantize_a16w4(w, group)
+        op = ops.GemmWQ(K, N, 4, group, max_m=M).prepare(q.cuda(), s.cuda(), z.cuda())
+        hs.append((op, Q.unpack_u4x2(q.numpy(), N), s, z, group))
+    ws = ops.Workspace()
+    a = (torch.rand(M, K, generator=g) * 2 - 1).to(torch.bfloat16)
+    for _ in range(2):      # plan A, plan B, then launch A again
+        for op, qu, s, z, group in hs:
+            out = op(a.cuda(), ws)
+            torch.cuda.synchronize()
+            ref = Q.gemm_wq_math(a.float().numpy(), qu, s.float().numpy(), z.float().numpy(), group)
+            assert Q.err_min_abs_rel(ref, out.float().cpu().numpy()) <= TOL

@@ -20,6 +20,9 @@ def _lib():
     lib.as_test_gemm.restype = C.c_int
     lib.as_test_gemm.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
                                  C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.as_test_gemm_binary.restype = C.c_int
+    lib.as_test_gemm_binary.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
+                                        C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.as_test_span_attn.restype = C.c_int
     lib.as_test_span_attn.argtypes = [C.c_int] * 9 + [C.c_void_p, C.c_void_p]
     lib.as_test_registered.restype = C.c_int
@@ -116,3 +119,75 @@ def test_span_attention_operator_decode_loop(span, steps):
             # probabilities fed to the tensor core (2^-9 relative each, weighted by |V| <= vmax)
             vmax = float(np.abs(x[:t + 1, :, nH + nG:]).max())
             assert np.all(np.abs(got[t] - ref) <= 2e-3 + 2.0 ** -7 * np.abs(ref) + 2.0 ** -9 * vmax), (t, np.abs(got[t] - ref).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("op", ["Gemm", "GemmA16W4"])
+def test_gemm_operator_binary_add_residual(op):
+    """the default do_binary_add_fused graph emits Gemm(x, residual) with binary_type = ADD for o_proj / down_proj
+    (qwen_v15.py:280-286,340; GemmOpBase gemm_op.cpp:73-136): the second input must be added, not dropped."""
+    from b200spark import quantize as PQ
+    lib = _lib()
+    M, K, N = 5, 1024, 640
+    g = torch.Generator().manual_seed(77)
+    w = (torch.randn(K, N, generator=g) * 0.02).to(torch.bfloat16)
+    a = (torch.rand(M, K, generator=g) * 2 - 1).to(torch.bfloat16)
+    res = torch.randn(M, N, generator=g).to(torch.bfloat16)
+    out = np.zeros((M, N), np.int16)
+    if op == "Gemm":
+        q, s, z, wdt, qn = w, None, None, 9, _bf16_np(w)
+        ref = a.float().numpy().astype(np.float64) @ w.float().numpy().astype(np.float64)
+    else:
+        q, s, z = PQ.quantize_a16w4(w, -1)
+        wdt, qn = 10, q.contiguous().numpy()
+        ref = Q.gemm_wq_math(a.float().numpy(), Q.unpack_u4x2(q.numpy(), N), s.float().numpy(), z.float().numpy(), -1)
+    sn = _bf16_np(s) if s is not None else None
+    zn = _bf16_np(z) if z is not None else None
+    an, rn = _bf16_np(a), _bf16_np(res)
+    rc = lib.as_test_gemm_binary(op.encode(), M, N, K, -1, 0, 1.0, an.ctypes.data, qn.ctypes.data, wdt,
+                                 sn.ctypes.data if sn is not None else None, zn.ctypes.data if zn is not None else None, None,
+                                 rn.ctypes.data, 1, out.ctypes.data)
+    assert rc == 0, rc
+    got = torch.from_numpy(out).view(torch.bfloat16).float().numpy()
+    assert Q.err_min_abs_rel((ref + res.float().numpy()).astype(np.float32), got) <= 2e-2
+    # binary_type MUL is not implemented by GemmOpGPU either: PARAM_ERROR, not a silent drop
+    rc = lib.as_test_gemm_binary(op.encode(), M, N, K, -1, 0, 1.0, an.ctypes.data, qn.ctypes.data, wdt,
+                                 sn.ctypes.data if sn is not None else None, zn.ctypes.data if zn is not None else None, None,
+                                 rn.ctypes.data, 2, out.ctypes.data)
+    assert rc == 2
+
+
+@pytest.mark.gpu
+def test_span_attention_operator_needs_layer_number_in_name():
+    """span_attn_op.cpp:183-187: the layer index is parsed from the op name; a name without one is ALLSPARK_PARAM_ERROR."""
+    lib = _lib()
+    qkv = np.zeros((1, 1, (8 + 4) * 128), np.int16)
+    out = np.zeros((1, 1, 8 * 128), np.int16)
+    assert lib.as_test_span_attn(1, 1, 8, 2, 16, 0, 64, 2, -1, qkv.ctypes.data, out.ctypes.data) == 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [KV.QUANT_I8, KV.QUANT_U4])
+@pytest.mark.parametrize("layer", [0, 2])
+def test_span_attention_operator_quantized_cache_modes(mode, layer):
+    """DecOptMQA with AsCacheQuantI8 / AsCacheQuantU4 spans on layer 0 and on a later layer of a 3-layer cache (the op finds
+    its layer through the op name), 40 decode steps with span 16 (spans claimed on demand, pinned staging ring wraps)."""
+    lib = _lib()
+    B, nH, nG, span, steps = 3, 8, 2, 16, 40
+    W, OW = (nH + 2 * nG) * 128, nH * 128
+    rng = np.random.default_rng(mode * 10 + layer)
+    qkv = torch.from_numpy(rng.standard_normal((steps, B, W)).astype(np.float32)).to(torch.bfloat16)
+    out = np.zeros((steps, B, OW), np.int16)
+    rc = lib.as_test_span_attn(B, steps, nH, nG, span, mode, 256, 3, layer, _bf16_np(qkv).ctypes.data, out.ctypes.data)
+    assert rc == 0, rc
+    got = torch.from_numpy(out).view(torch.bfloat16).float().numpy().reshape(steps, B, nH, 128)
+    kref, vref = KV.SpanCacheRef(mode, span, nG), KV.SpanCacheRef(mode, span, nG)
+    for _ in range(B):
+        kref.add_sequence(); vref.add_sequence()
+    x = qkv.float().numpy().reshape(steps, B, nH + 2 * nG, 128)
+    for t in range(steps):
+        for b in range(B):
+            kref.append(b, t, x[t, b, nH:nH + nG]); vref.append(b, t, x[t, b, nH + nG:])
+        if t in (0, 1, span - 1, span, steps - 1):
+            ref = KV.attention_ref(x[t, :, :nH], kref, vref, [t + 1] * B, nH, 1.0 / np.sqrt(128))
+            assert np.all(np.abs(got[t] - ref) <= 2e-3 + 2.0 ** -7 * np.abs(ref)), (t, np.abs(got[t] - ref).max())

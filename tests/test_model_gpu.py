@@ -111,3 +111,35 @@ def test_glue_ops():
         r = torch.cat([xin[bb, :, :64] * cs - xin[bb, :, 64:] * sn, xin[bb, :, 64:] * cs + xin[bb, :, :64] * sn], -1)
         assert (out[bb, :nH + nG] - r[:nH + nG].float()).abs().max().item() <= 2e-2
         assert torch.equal(out[bb, nH + nG:], xin[bb, nH + nG:].float())  # V untouched
+
+
+@pytest.mark.parametrize("B", [1, 64])
+def test_full_width_qwen2_7b_layer_and_lm_head(B):
+    """model-level parity was only checked on the 512-wide TINY config.  ONE full-width Qwen2-7B layer
+    (hidden 3584, 28/4 heads, inter 18944, int4 per-channel — exactly the launches bench.py times at this batch: the
+    mma.sync GEMV family at B=1, the tcgen05 family + persistent gate/up pair at B=64) + final norm + the 152064-wide bf16
+    lm_head + argmax, three decode steps from an empty cache, against the reference-CPU-path oracle."""
+    from b200spark import model
+    steps = 3
+    st = model.DecodeStack(model.QWEN2_7B, B, 32, wbits=4, group=-1, kv="none", span=16, keep_ref=True, layers=1)
+    ref = DR.from_stack(st, KV.QUANT_NONE)
+    ref.reset(B)
+    ids = torch.randint(0, model.QWEN2_7B.vocab, (B,), generator=torch.Generator().manual_seed(4321), dtype=torch.int64)
+    for t in range(steps):
+        st.ids.copy_(ids.cuda())
+        nxt = st.step().cpu()
+        torch.cuda.synchronize()
+        glog = st.logits.float().cpu()
+        rlog, rnext = ref.step(ids, [t] * B)
+        tol = 1e-2 * rlog.abs().max().item()
+        err = (glog - rlog).abs().max().item()
+        assert err <= tol, (t, err, tol)
+        assert torch.equal(nxt, torch.argmax(glog, dim=-1))
+        top2 = torch.topk(rlog, 2, dim=-1).values
+        agree = 0
+        for b in range(B):
+            if (top2[b, 0] - top2[b, 1]).item() > 2 * tol:
+                assert nxt[b].item() == rnext[b].item(), (t, b)
+                agree += 1
+        ids = nxt
+    assert st.lens_old.cpu().tolist() == [steps] * B
