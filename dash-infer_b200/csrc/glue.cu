@@ -154,6 +154,21 @@ __global__ void lens_add_kernel(int32_t* lens, int batch, int delta) {
   if (i < batch) lens[i] += delta;
 }
 
+// vocab-split lm_head: pick the global winner among the ranks' (max, argmax) pairs; ties -> lowest rank == lowest vocab id
+__global__ void argmax_merge_kernel(int64_t* ids_out, const float* vals, const int64_t* ids, int nranks, int batch) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  float best = vals[b];
+  int64_t bid = ids[b];
+  for (int r = 1; r < nranks; ++r) {
+    const float v = vals[(size_t)r * batch + b];
+    if (v > best) { best = v; bid = ids[(size_t)r * batch + b]; }
+  }
+  ids_out[b] = bid;
+}
+
 }  // namespace b2
 
 using namespace b2;
@@ -216,6 +231,13 @@ int b2_argmax_shard(int64_t* ids_out, float* vals_out, const void* logits, int b
   if (!ids_out || !vals_out || !logits || batch <= 0 || n <= 0) return B2_ERR_PARAM;
   B2_LAUNCH_CHECK("argmax_shard", launch(argmax_kernel, dim3(batch), dim3(1024), 0, (cudaStream_t)stream, true, ids_out, vals_out,
                                          (const __nv_bfloat16*)logits, n, ld, id_offset));
+  return B2_OK;
+}
+
+int b2_argmax_merge(int64_t* ids_out, const float* all_vals, const int64_t* all_ids, int nranks, int batch, void* stream) {
+  if (!ids_out || !all_vals || !all_ids || nranks <= 0 || batch <= 0) return B2_ERR_PARAM;
+  B2_LAUNCH_CHECK("argmax_merge", launch(argmax_merge_kernel, dim3((batch + 127) / 128), dim3(128), 0, (cudaStream_t)stream, true,
+                                         ids_out, all_vals, all_ids, nranks, batch));
   return B2_OK;
 }
 

@@ -20,11 +20,13 @@
 // Roofline: HBM-bound; algorithmic bytes/launch = K*N*wbits/8 + 4*G*N + 2*M*(K+N).
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <new>
 
 #include "b2_common.cuh"
+#include "comm_shared.cuh"
 #include "wq_gemm_shared.cuh"
 
 namespace b2 {
@@ -58,6 +60,9 @@ struct GemmParams {
   int norm_parts;
   float norm_inv_hidden, norm_eps;
   float* sumsq_out;
+  // optional fused all-reduce of the output over tensor-parallel ranks (b2_gemm_wq_run_allreduce)
+  int comm_on;
+  CommDev comm;
 };
 
 template <int WBITS>
@@ -368,6 +373,76 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
       else {
         cp[0] = __float2bfloat16(v0);
         if ((n + 1) < p.N) cp[1] = __float2bfloat16(v1);
+      }
+    }
+    return;
+  }
+  if (p.comm_on) {
+    // ---- fused all-reduce over the tensor-parallel ranks (row-parallel o_proj / down_proj): this CTA holds the final
+    // partial sums of tile `ng` of THIS rank.  Push them (bf16, like the reference's partial outputs) into slot[rank] of
+    // every rank's exchange buffer, raise the tile's flag there, wait for the other ranks' tiles in local memory, sum the
+    // nranks partials in rank order in fp32, add the residual once, round once.  Tiles are independent: the exchange of
+    // this tile overlaps the weight streaming of the n-groups still running.  N is even (checked on the host).
+    const CommDev& cd = p.comm;
+    const unsigned epoch = *reinterpret_cast<volatile unsigned*>(cd.epoch);
+    const unsigned want = epoch + 1;
+    const int par = epoch & 1;
+    const size_t my_slot = comm_slot_offset(cd, par, cd.rank);
+    for (int i = ctid; i < p.M * (kBN / 2); i += kWarps * 32) {
+      const int m = i >> 6, np = i & 63;
+      const int n = ng * kBN + np * 2;
+      if (n >= p.N) continue;
+      float v0 = fs[m * kBN + np * 2] * p.alpha, v1 = fs[m * kBN + np * 2 + 1] * p.alpha;
+      if (p.bias) {
+        v0 += __bfloat162float(p.bias[n]);
+        v1 += __bfloat162float(p.bias[n + 1]);
+      }
+      const uint32_t pk = pack_bf16x2(v0, v1);
+      const size_t off = my_slot + ((size_t)m * p.N + n) * 2;
+      for (int r = 0; r < cd.nranks; ++r) *reinterpret_cast<uint32_t*>(cd.peer[(cd.rank + r) % cd.nranks] + off) = pk;
+    }
+    __threadfence_system();
+    named_bar_sync(1, kWarps * 32);
+    __shared__ int s_comm_ok;
+    if (ctid == 0) s_comm_ok = 1;
+    if (ctid < cd.nranks) {
+      unsigned* f = reinterpret_cast<unsigned*>(cd.peer[ctid] + comm_flag_offset(cd, par, cd.rank, ng));
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(want) : "memory");
+    }
+    named_bar_sync(1, kWarps * 32);
+    if (ctid < cd.nranks) {
+      const unsigned* f = reinterpret_cast<const unsigned*>(cd.peer[cd.rank] + comm_flag_offset(cd, par, ctid, ng));
+      if (!wait_flag(f, want, cd.timeout_ns, cd.error)) s_comm_ok = 0;
+    }
+    named_bar_sync(1, kWarps * 32);
+    if (s_comm_ok) {
+      const uint8_t* base = cd.peer[cd.rank];
+      for (int i = ctid; i < p.M * (kBN / 2); i += kWarps * 32) {
+        const int m = i >> 6, np = i & 63;
+        const int n = ng * kBN + np * 2;
+        if (n >= p.N) continue;
+        const size_t eo = ((size_t)m * p.N + n) * 2;
+        float a0 = 0.f, a1 = 0.f;
+        for (int r = 0; r < cd.nranks; ++r) {
+          const uint32_t v = __ldcg(reinterpret_cast<const uint32_t*>(base + comm_slot_offset(cd, par, r) + eo));
+          a0 += bf16_lo(v);
+          a1 += bf16_hi(v);
+        }
+        if (p.residual) {
+          const uint32_t v = *reinterpret_cast<const uint32_t*>(p.residual + (int64_t)m * p.ldc + n);
+          a0 += bf16_lo(v);
+          a1 += bf16_hi(v);
+        }
+        *reinterpret_cast<uint32_t*>(p.C + (int64_t)m * p.ldc + n) = pack_bf16x2(a0, a1);
+      }
+    }
+    named_bar_sync(1, kWarps * 32);
+    if (ctid == 0) {  // the last tile of the launch advances the communicator's epoch
+      __threadfence();
+      if (atomicAdd(cd.done, 1u) == (unsigned)(p.NG - 1)) {
+        *cd.done = 0;
+        __threadfence();
+        *reinterpret_cast<volatile unsigned*>(cd.epoch) = want;
       }
     }
     return;
@@ -812,9 +887,35 @@ int b2_gemm_wq_run(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, int64_t 
   return b2_gemm_wq_run_fused(h, A, lda, C, ldc, M, bias, residual, activation, alpha, workspace, workspace_bytes, nullptr, stream_);
 }
 
+extern "C" const void* b2_comm_device_view(b2_comm_t c);
+
+static int run_impl(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, int64_t ldc, int M, const void* bias,
+                    const void* residual, int activation, float alpha, void* workspace, size_t workspace_bytes,
+                    const b2_gemm_fuse* fuse, const CommDev* comm, void* stream_);
+
 int b2_gemm_wq_run_fused(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, int64_t ldc, int M, const void* bias,
                          const void* residual, int activation, float alpha, void* workspace, size_t workspace_bytes,
                          const b2_gemm_fuse* fuse, void* stream_) {
+  return run_impl(h, A, lda, C, ldc, M, bias, residual, activation, alpha, workspace, workspace_bytes, fuse, nullptr, stream_);
+}
+
+int b2_gemm_wq_run_allreduce(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, int64_t ldc, int M, const void* bias,
+                             const void* residual, float alpha, void* workspace, size_t workspace_bytes, b2_comm_t comm,
+                             void* stream_) {
+  const CommDev* cd = static_cast<const CommDev*>(b2_comm_device_view(comm));
+  if (!h || !cd) return B2_ERR_PARAM;
+  for (int r = 0; r < cd->nranks; ++r)
+    if (!cd->peer[r]) return B2_ERR_RUNTIME;  // communicator not connected
+  // the GEMV path only (one launch, M <= 16), even N, plain [M, N] output, every tile has a flag, payload fits a slot
+  if (M > 16 || h->pair || (h->d.N & 1) || ldc != h->d.N || h->NG > kCommMaxChunks) return B2_ERR_UNSUPPORTED;
+  if ((size_t)M * h->d.N * 2 > cd->max_bytes) return B2_ERR_LIMIT;
+  if (((uintptr_t)C & 3) || (residual && ((uintptr_t)residual & 3))) return B2_ERR_UNSUPPORTED;
+  return run_impl(h, A, lda, C, ldc, M, bias, residual, B2_ACT_NONE, alpha, workspace, workspace_bytes, nullptr, cd, stream_);
+}
+
+static int run_impl(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, int64_t ldc, int M, const void* bias,
+                    const void* residual, int activation, float alpha, void* workspace, size_t workspace_bytes,
+                    const b2_gemm_fuse* fuse, const CommDev* comm, void* stream_) {
   if (!h || !A || !C || M <= 0) return B2_ERR_PARAM;
   const bool fused = fuse && (fuse->norm_sumsq || fuse->sumsq_out);
   if (fused && (M > 16 || h->pair && fuse->sumsq_out)) return B2_ERR_UNSUPPORTED;
@@ -828,7 +929,7 @@ int b2_gemm_wq_run_fused(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, in
   if (workspace_bytes < b2_gemm_wq_workspace_bytes(h, M)) return B2_ERR_PARAM;
   cudaStream_t stream = (cudaStream_t)stream_;
   const bool grouped = h->group_tiles > 0;
-  if (use_tc(h, M)) {  // decode batches 17..: tcgen05 path, 64 rows per launch
+  if (use_tc(h, M) && !comm) {  // decode batches 17..: tcgen05 path, 64 rows per launch
     if (int st = make_tc_plan(h)) return st;
     if (h->tc_S > 1 && !workspace) return B2_ERR_PARAM;
     for (int m0 = 0; m0 < M; m0 += kTcMaxM) {
@@ -881,6 +982,9 @@ int b2_gemm_wq_run_fused(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, in
     p.norm_inv_hidden = fuse && fuse->norm_hidden > 0 ? 1.0f / (float)fuse->norm_hidden : 0.f;
     p.norm_eps = fuse ? fuse->norm_eps : 0.f;
     p.sumsq_out = fuse ? fuse->sumsq_out : nullptr;
+    p.comm_on = comm ? 1 : 0;
+    if (comm) p.comm = *comm;
+    else memset(&p.comm, 0, sizeof(p.comm));
     gemm_kernel_t kern = pick_kernel(h->d.wbits, grouped, 1 << mti);
     cudaError_t e = launch(kern, dim3(h->NG * pl.S), dim3(kThreads), (size_t)pl.smem, stream, true, p);
     if (e != cudaSuccess) {

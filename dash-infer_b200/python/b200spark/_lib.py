@@ -15,7 +15,9 @@ SYMBOLS = [
     "b2_gemm_wq_algo_bytes",
     "b2_span_bytes", "b2_span_cache_append", "b2_span_attn_create", "b2_span_attn_destroy",
     "b2_span_attn_workspace_bytes", "b2_span_attn_run", "b2_span_attn_algo_bytes",
-    "b2_rmsnorm", "b2_rotary", "b2_binary", "b2_embedding", "b2_argmax", "b2_argmax_shard", "b2_lens_add",
+    "b2_rmsnorm", "b2_rotary", "b2_binary", "b2_embedding", "b2_argmax", "b2_argmax_shard", "b2_argmax_merge", "b2_lens_add",
+    "b2_comm_create", "b2_comm_destroy", "b2_comm_buffer_bytes", "b2_comm_export", "b2_comm_connect", "b2_comm_connect_pointers",
+    "b2_comm_local_buffer", "b2_comm_error", "b2_allreduce", "b2_allgather", "b2_gemm_wq_run_allreduce",
 ]
 
 
@@ -44,6 +46,7 @@ ACT_NONE, ACT_TANH, ACT_GELU_ERF, ACT_GELU_TANH, ACT_RELU, ACT_SILU, ACT_SIGMOID
 ACT_SWIGLU = 100
 BIN_ADD, BIN_MUL = 1, 2
 KV_NONE, KV_I8, KV_U4 = 0, 1, 2
+COMM_HANDLE_BYTES = 64
 
 
 class B2Error(RuntimeError):
@@ -87,6 +90,18 @@ def _load():
         "b2_argmax": (i32, [vp, vp, i32, i32, i64, vp]),
         "b2_argmax_shard": (i32, [vp, vp, vp, i32, i32, i64, i64, vp]),
         "b2_lens_add": (i32, [vp, i32, i32, vp]),
+        "b2_argmax_merge": (i32, [vp, vp, vp, i32, i32, vp]),
+        "b2_comm_create": (i32, [C.POINTER(vp), i32, i32, sz]),
+        "b2_comm_destroy": (i32, [vp]),
+        "b2_comm_buffer_bytes": (sz, [i32, sz]),
+        "b2_comm_export": (i32, [vp, vp]),
+        "b2_comm_connect": (i32, [vp, vp]),
+        "b2_comm_connect_pointers": (i32, [vp, vp]),
+        "b2_comm_local_buffer": (vp, [vp]),
+        "b2_comm_error": (i32, [vp]),
+        "b2_allreduce": (i32, [vp, vp, vp, vp, i64, i32, vp]),
+        "b2_allgather": (i32, [vp, vp, vp, i32, vp]),
+        "b2_gemm_wq_run_allreduce": (i32, [vp, vp, i64, vp, i64, i32, vp, vp, f32, vp, sz, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here == ABI drift: fail loudly

@@ -118,12 +118,19 @@ class _RefView:
 
 class DecodeStack:
     def __init__(self, cfg, batch, max_len, wbits=4, group=-1, kv="none", span=128, seed=1234, device="cuda",
-                 keep_ref=False, layers=None, tp_rank=0, tp_size=1, tp_group=None, fuse_swiglu=True, fuse_norm=False):
+                 keep_ref=False, layers=None, tp_rank=0, tp_size=1, tp_group=None, fuse_swiglu=True, fuse_norm=False,
+                 collective=None, comm=None):
         """tp_size > 1: the reference's tensor-parallel layout (QKV/gate/up column split, o/down row split + all-reduce,
         vocab-split lm_head + B-element all-gather); every rank builds the SAME full synthetic weights from `seed` and
         keeps its shard, exactly like the reference splits an already-quantized checkpoint."""
         self.cfg, self.B, self.max_len = cfg, batch, max_len
         self.tp_rank, self.tp, self.tp_group = tp_rank, tp_size, tp_group
+        # tensor-parallel exchange: "fused" = all-reduce inside the row-parallel GEMV's epilogue (b2_gemm_wq_run_allreduce;
+        # batches <= 16, else it degrades to "b2"), "b2" = GEMM + b2_allreduce (one-shot over NVLink peer memory, residual
+        # fused), "nccl" = torch.distributed all_reduce + copy (the baseline the reference's AllReduceOp amounts to)
+        import os
+        self.collective = collective or os.environ.get("B2_TP_COLLECTIVE", "fused")
+        self.comm = comm
         self.fuse_swiglu = fuse_swiglu
         self.group_size = group
         self.device = device
@@ -175,6 +182,8 @@ class DecodeStack:
                           ao=torch.empty(batch, nHl * 128, **bf), gate=torch.empty(batch, self.I_l, **bf),
                           up=torch.empty(batch, self.I_l, **bf), logits=torch.empty(batch, self.vocab_l, **bf))
         if tp > 1:
+            if self.collective != "nccl" and self.comm is None:
+                self.comm = ops.Comm(tp_rank, tp, max(batch * H * 2, 4096)).connect_group(tp_group)
             self._bufs["part"] = torch.empty(batch, H, **bf)             # row-split partial sums (all-reduced)
             self.loc_ids = torch.empty(batch, dtype=torch.int64, device=device)
             self.loc_val = torch.empty(batch, dtype=torch.float32, device=device)
@@ -224,24 +233,38 @@ class DecodeStack:
 
     # ------------------------------------------------------------------ one decode step (eager or captured)
     def _row_parallel(self, lin, inp, n):
-        """o_proj / down_proj.  TP=1: residual fused in the GEMM epilogue.  TP>1: partial sums (rank 0 carries the
-        residual), all-reduce over NVLink (reference: AllReduceOp after o_proj and down_proj, allreduce_op.cpp:73-115 —
-        here stream-ordered, no host sync)."""
-        import torch.distributed as dist
+        """o_proj / down_proj.  TP=1: residual fused in the GEMM epilogue.  TP>1: per-rank partial sums exchanged over NVLink
+        (reference: AllReduceOp after o_proj and down_proj, allreduce_op.cpp:73-115 — here stream-ordered, no host sync);
+        the residual is added once, after the sum, on every rank."""
         if self.tp == 1:
             lin(inp, self.ws, out=self.x, residual=self.x)
             return n + 1
-        lin(inp, self.ws, out=self.part, residual=self.x if self.tp_rank == 0 else None)
-        self._allreduce(self.part, out=self.x)
-        return n + 1
+        if self.collective == "nccl":
+            import torch.distributed as dist
+            lin(inp, self.ws, out=self.part, residual=self.x if self.tp_rank == 0 else None)
+            dist.all_reduce(self.part, group=self.tp_group)
+            self.x.copy_(self.part)
+            return n + 1
+        if self.collective == "fused" and lin.op.run_allreduce(inp, self.ws, self.comm, out=self.x, residual=self.x):
+            return n + 1
+        lin(inp, self.ws, out=self.part)
+        self.comm.allreduce(self.part, out=self.x, residual=self.x)
+        return n + 2
 
-    collective_impl = "nccl all_reduce + copy"
+    @property
+    def collective_impl(self):
+        return {"nccl": "nccl all_reduce + copy", "b2": "GEMM + b2_allreduce (one-shot, NVLink peer memory)",
+                "fused": "all-reduce fused into the row-parallel GEMV epilogue (one-shot, NVLink peer memory)"}[self.collective]
 
     def _allreduce(self, t, out=None):
-        import torch.distributed as dist
-        dist.all_reduce(t, group=self.tp_group)
-        if out is not None:
-            out.copy_(t)
+        """the exchange alone (collective_probe)"""
+        if self.collective == "nccl":
+            import torch.distributed as dist
+            dist.all_reduce(t, group=self.tp_group)
+            if out is not None:
+                out.copy_(t)
+        else:
+            self.comm.allreduce(t, out=out if out is not None else t)
 
     def _step_ops(self):
         cfg, ws = self.cfg, self.ws
@@ -282,12 +305,15 @@ class DecodeStack:
         if self.tp == 1:
             ops.argmax(self.logits, out=self.next_ids); n += 1
         else:  # vocab-split lm_head: local (max, argmax) + B-element all-gather instead of all-reducing 152064 logits
-            import torch.distributed as dist
             ops.argmax_shard(self.logits, self.tp_rank * self.vocab_l, self.loc_ids, self.loc_val); n += 1
-            dist.all_gather_into_tensor(self.all_val, self.loc_val, group=self.tp_group)
-            dist.all_gather_into_tensor(self.all_ids, self.loc_ids, group=self.tp_group)
-            win = torch.argmax(self.all_val, dim=0)  # lowest rank on ties == lowest vocab index
-            self.next_ids.copy_(torch.gather(self.all_ids, 0, win[None, :])[0])
+            if self.collective == "nccl":
+                import torch.distributed as dist
+                dist.all_gather_into_tensor(self.all_val, self.loc_val, group=self.tp_group)
+                dist.all_gather_into_tensor(self.all_ids, self.loc_ids, group=self.tp_group)
+            else:
+                self.comm.allgather(self.loc_val, self.all_val); n += 1
+                self.comm.allgather(self.loc_ids, self.all_ids); n += 1
+            ops.argmax_merge(self.all_val, self.all_ids, out=self.next_ids); n += 1  # lowest rank on ties == lowest vocab id
         ops.lens_add(self.lens_old, 1); n += 1
         ops.lens_add(self.lens_new, 1); n += 1
         # rows per launch above batch 16: 64 on the tcgen05 path (per-channel int4/int8, bf16 lm_head), 16 for sub-channel
@@ -328,8 +354,12 @@ class DecodeStack:
         def ops_():
             for _ in range(2 * len(self.layers)):
                 self._allreduce(self.part)
-            dist_.all_gather_into_tensor(self.all_val, self.loc_val, group=self.tp_group)
-            dist_.all_gather_into_tensor(self.all_ids, self.loc_ids, group=self.tp_group)
+            if self.collective == "nccl":
+                dist_.all_gather_into_tensor(self.all_val, self.loc_val, group=self.tp_group)
+                dist_.all_gather_into_tensor(self.all_ids, self.loc_ids, group=self.tp_group)
+            else:
+                self.comm.allgather(self.loc_val, self.all_val)
+                self.comm.allgather(self.loc_ids, self.all_ids)
         ops_()
         torch.cuda.synchronize()
         with torch.cuda.graph(g):

@@ -104,10 +104,73 @@ class GemmWQ:
                                        float(alpha), _ptr(wsb), wsb.numel(), C.byref(f), _stream()), "b2_gemm_wq_run_fused")
         return out
 
+    def run_allreduce(self, a, ws, comm, out, residual=None, alpha=1.0):
+        """Row-parallel projection fused with its all-reduce over `comm` (b2_gemm_wq_run_allreduce).  Returns False when the
+        configuration is not covered (M > 16, ...): the caller then runs the GEMM and b2_allreduce separately."""
+        M = a.numel() // a.shape[-1]
+        wsb = ws.reserve(self.workspace_bytes(M))
+        st = lib.b2_gemm_wq_run_allreduce(self.h, _ptr(a), a.stride(-2) if a.dim() > 1 else self.K, _ptr(out),
+                                          out.stride(-2) if out.dim() > 1 else self.N, M, _ptr(self.bias), _ptr(residual), float(alpha),
+                                          _ptr(wsb), wsb.numel(), comm.h, _stream())
+        if st == 6:  # B2_ERR_UNSUPPORTED
+            return False
+        check(st, "b2_gemm_wq_run_allreduce")
+        return True
+
     def __del__(self):
         try:
             if self.h:
                 lib.b2_gemm_wq_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class Comm:
+    """Tensor-parallel communicator over NVLink peer memory (b2_comm_*).  `connect_group` exchanges the CUDA IPC handles
+    over a torch.distributed process group (host side plumbing only); `connect_local` wires communicators that live in the
+    same process (tests: two ranks on one GPU)."""
+
+    def __init__(self, rank, nranks, max_bytes):
+        self.rank, self.nranks, self.max_bytes = rank, nranks, int(max_bytes)
+        self.h = C.c_void_p()
+        check(lib.b2_comm_create(C.byref(self.h), rank, nranks, self.max_bytes), "b2_comm_create")
+
+    def connect_group(self, group=None):
+        import torch.distributed as dist
+        buf = C.create_string_buffer(_lib.COMM_HANDLE_BYTES)
+        check(lib.b2_comm_export(self.h, buf), "b2_comm_export")
+        handles = [None] * self.nranks
+        dist.all_gather_object(handles, bytes(buf.raw), group=group)
+        allh = b"".join(handles)
+        check(lib.b2_comm_connect(self.h, allh), "b2_comm_connect")
+        dist.barrier(group=group)
+        return self
+
+    @staticmethod
+    def connect_local(comms):
+        n = len(comms)
+        ptrs = (C.c_void_p * n)(*[lib.b2_comm_local_buffer(c.h) for c in comms])
+        for c in comms:
+            check(lib.b2_comm_connect_pointers(c.h, ptrs), "b2_comm_connect_pointers")
+        return comms
+
+    def allreduce(self, t, out=None, residual=None):
+        out = t if out is None else out
+        check(lib.b2_allreduce(self.h, _ptr(out), _ptr(t), _ptr(residual), t.numel(), DT_BF16, _stream()), "b2_allreduce")
+        return out
+
+    def allgather(self, t, out):
+        check(lib.b2_allgather(self.h, _ptr(out), _ptr(t), t.numel() * t.element_size(), _stream()), "b2_allgather")
+        return out
+
+    def check_error(self):
+        check(lib.b2_comm_error(self.h), "b2_comm_error (a peer did not arrive within B2_COMM_TIMEOUT_MS)")
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib.b2_comm_destroy(self.h)
                 self.h = None
         except Exception:
             pass
@@ -226,6 +289,12 @@ def argmax_shard(logits, id_offset, ids_out, vals_out):
     check(lib.b2_argmax_shard(_ptr(ids_out), _ptr(vals_out), _ptr(logits), B, n, logits.stride(0), int(id_offset), _stream()),
           "b2_argmax_shard")
     return ids_out, vals_out
+
+
+def argmax_merge(all_vals, all_ids, out):
+    tp, B = all_vals.shape
+    check(lib.b2_argmax_merge(_ptr(out), _ptr(all_vals), _ptr(all_ids), tp, B, _stream()), "b2_argmax_merge")
+    return out
 
 
 def lens_add(lens, delta):

@@ -20,6 +20,8 @@
  *                           csrc/core/kernel/cuda/cache/decoder_cache_append.cuh:102-185
  *   b2_span_attn_*        span::CreateHandle/GetDeviceWorkspaceSize/Run/DestroyHandle
  *                           span-attention/include/spanattn/span_attn.h:108-175
+ *   b2_comm_*, b2_allreduce, b2_allgather, b2_gemm_wq_run_allreduce
+ *                         AllReduceOp::Forward  csrc/core/operator/nccl/allreduce/allreduce_op.cpp:73-115
  *   b2_rmsnorm, b2_rotary, b2_binary, b2_embedding, b2_argmax ("next" rows)
  *                         LayerNormNoBeta / Rotary / Binary / EmbeddingT5 / GenerateOp(top_k=1)
  *                           csrc/core/kernel/cuda/layernorm.cu:86, rotary.cu:23, binary.cu
@@ -201,8 +203,48 @@ int b2_argmax(int64_t* ids_out, const void* logits, int batch, int n, int64_t ld
  * value (fp32) so the ranks can pick the global winner with a B-element all-gather instead of all-reducing logits. */
 int b2_argmax_shard(int64_t* ids_out, float* vals_out, const void* logits, int batch, int n, int64_t ld,
                     int64_t id_offset, void* stream);
+/* ids_out[b] = all_ids[r*][b] with r* = the rank of the largest all_vals[r][b] (lowest rank on ties): the second half of the
+ * vocab-split argmax after the (max, argmax) pairs were all-gathered ([nranks][batch] each). */
+int b2_argmax_merge(int64_t* ids_out, const float* all_vals, const int64_t* all_ids, int nranks, int batch, void* stream);
 /* lens[b] += delta for b < batch (keeps sequence lengths device-resident under CUDA graphs) */
 int b2_lens_add(int32_t* lens, int batch, int delta, void* stream);
+
+/* =====================================================================================
+ * Tensor-parallel exchange over NVLink peer memory (replaces AllReduceOp / ncclAllReduce for the decode step's
+ * activations, csrc/core/operator/nccl/allreduce/allreduce_op.cpp:73-115).  One communicator per rank, one process per
+ * GPU.  Every rank owns an exchange buffer; the peers map it (CUDA IPC handles exchanged by the caller, or any table of
+ * peer pointers).  All calls are stream-ordered, never synchronise the host and are CUDA-graph replayable; every rank
+ * must issue the same sequence of exchanges on a communicator.  FT = bf16; sums are fp32 in rank order (deterministic).
+ * ===================================================================================== */
+typedef struct b2_comm* b2_comm_t;
+#define B2_COMM_HANDLE_BYTES 64 /* sizeof(cudaIpcMemHandle_t) */
+/* max_bytes: largest payload of one exchange (per rank).  Allocates and zeroes this rank's exchange buffer. */
+int b2_comm_create(b2_comm_t* comm, int rank, int nranks, size_t max_bytes);
+int b2_comm_destroy(b2_comm_t comm);
+size_t b2_comm_buffer_bytes(int nranks, size_t max_bytes);
+/* IPC route: export this rank's handle (B2_COMM_HANDLE_BYTES), all-gather the handles on the host (any transport), then
+ * connect with the nranks handles in rank order. */
+int b2_comm_export(b2_comm_t comm, void* handle_out);
+int b2_comm_connect(b2_comm_t comm, const void* all_handles);
+/* Pointer route: peer_buffers[r] = rank r's exchange buffer as addressable from this process (b2_comm_local_buffer of
+ * that rank's communicator: same process with peer access, symmetric memory, ...).  peer_buffers[rank] is ignored. */
+int b2_comm_connect_pointers(b2_comm_t comm, void* const* peer_buffers);
+void* b2_comm_local_buffer(b2_comm_t comm);
+/* B2_OK, or B2_ERR_RUNTIME when a kernel gave up waiting for a peer (B2_COMM_TIMEOUT_MS, default 5000); synchronises. */
+int b2_comm_error(b2_comm_t comm);
+/* out[i] = sum over ranks of in[i] (+ residual[i], added once after the sum), count elements of FT (count % 8 == 0,
+ * 16-byte aligned pointers).  out may alias in or residual. */
+int b2_allreduce(b2_comm_t comm, void* out, const void* in, const void* residual, int64_t count, int ft, void* stream);
+/* out[r * bytes_per_rank ...] = rank r's `in` (small payloads: the vocab-split lm_head's per-rank (max, argmax)). */
+int b2_allgather(b2_comm_t comm, void* out, const void* in, int bytes_per_rank, void* stream);
+/* Row-parallel projection fused with its all-reduce: b2_gemm_wq_run where the partial sums of each 128-channel tile are
+ * pushed into the peers' exchange buffers by the tile's last CTA, which then waits for the peers' tiles, sums the nranks
+ * partials in rank order, adds `residual` once and writes C — one kernel instead of GEMV + all-reduce (+ copy), the
+ * exchange of a tile overlapping the weight streaming of the others.  M <= 16 (the GEMV path), activation NONE, no bias
+ * on ranks != 0 (pass bias only on rank 0).  Returns B2_ERR_UNSUPPORTED otherwise: call b2_gemm_wq_run + b2_allreduce. */
+int b2_gemm_wq_run_allreduce(b2_gemm_wq_t handle, const void* A, int64_t lda, void* C, int64_t ldc, int M, const void* bias,
+                             const void* residual, float alpha, void* workspace, size_t workspace_bytes, b2_comm_t comm,
+                             void* stream);
 
 /* Programmatic dependent launch (PDL) for every kernel launched by this library on this thread:
  * 1 = on (default), 0 = off. */

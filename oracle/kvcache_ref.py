@@ -1,12 +1,15 @@
 """Oracle: KV-cache span layout, I8/U4 row quantizer, cache append, fp32 paged attention.
 
-TEST INFRASTRUCTURE (see oracle/__init__.py).  **Parity unpinned**: the reference holds no golden
-vector or numeric test for quantized spans; this follows the CUDA sources.
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Pinned on the GPU box against the reference's OWN kernels
+(oracle/_ref/libdashinfer_ref.so = span-attention + the span-cache writers compiled from /root/reference by
+oracle/build_ref.py): tests/test_ref_pin_gpu.py compares span bytes, {zero, scale} params and attention outputs.  The
+reference holds no golden vector for quantized spans, so the pin is the reference executed.
 
 Follows (paths relative to /root/reference):
   * span-attention/src/cache_quant/impl_i8.cuh:29-142   QuantParam<I8>: ORIGIN -128, RANGE 255, clamp [-128,127], EPS 1e-5
   * span-attention/src/cache_quant/impl_u4.cuh:20-184   QuantParam<U4>: ORIGIN 0, RANGE 15, upper clamp only, lo nibble first
-  * span-attention/src/cache_quant/utils.cuh:24-45      Div (= __fdividef; IEEE division here), Rounding = rintf (CONFIG_CACHE_ROUND_RNI)
+  * span-attention/src/cache_quant/utils.cuh:24-45      Div (= __fdividef -> x * MUFU.RCP under --use_fast_math; IEEE reciprocal here),
+                                                        Rounding = rintf (CONFIG_CACHE_ROUND_RNI)
   * csrc/core/kernel/cuda/cache/decoder_cache_append.cuh:33-153  span = [nG, spanLen, HEAD] QT then [nG, spanLen] {f32 zero, f32 scale}
   * csrc/runtime/cache/virtual_cache.cpp:202-232        span byte size
   * span-attention/src/attn/quant.cuh:43-77             dequant x*scale - zero*scale (fp32)
@@ -30,24 +33,42 @@ def span_bytes(mode, span_len, n_groups, head=HEAD, ft_bytes=2):
     raise ValueError(mode)
 
 
+def _fma32(a, b, c):
+    """fl32(a * b + c) with ONE rounding: the fp32 x fp32 product is exact in fp64 (48 significant bits) and adding a
+    small integer-valued c keeps it exact, so rounding the fp64 sum to fp32 once is a true fused multiply-add."""
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+
 def quant_rows(x, mode):
     """x: fp32 [..., HEAD] (values already representable in the activation type).
-    Returns (q uint8/int8 [..., HEAD], zero f32 [...], scale f32 [...]).  All fp32, one op per line."""
+    Returns (q uint8/int8 [..., HEAD], zero f32 [...], scale f32 [...]).
+
+    Restates QuantParam<I8/U4>::Builder / Quant (impl_i8.cuh:54-61,106-140, impl_u4.cuh:146-182) AS COMPILED: the
+    reference builds its span-cache writers with --use_fast_math, so (SASS of QuantCacheAppendKernel in oracle/_ref)
+        qs = max((max - min) * fl(1/RANGE), 1e-5)            Div by the constant RANGE -> multiply by its reciprocal
+        r  = MUFU.RCP(qs)                                     __fdividef(x, qs) = x * rcp(qs)
+        qz = rint(clamp(fma(-min, r, ORIGIN)))                the add is contracted into the multiply
+        q  = rint(clamp(fma(x, r, qz)))
+    The only step a CPU cannot repeat bit for bit is MUFU.RCP (a <= 1 ulp hardware approximation); here it is the IEEE
+    fp32 reciprocal.  The two disagree only when fma(-min, r, ORIGIN) lands within an ulp of a .5 tie, which happens on
+    rows with max == -min (their zero point is exactly ORIGIN + RANGE/2): measured on the GPU box against the reference
+    kernel itself and recorded by tests/test_ref_pin_gpu.py."""
     x = x.astype(np.float32)
     mx = x.max(axis=-1)
     mn = x.min(axis=-1)
     if mode == QUANT_I8:
-        origin, rng, qmax, qmin = np.float32(-128), np.float32(255), np.float32(127), np.float32(-128)
+        origin, inv_rng, qmax, qmin = np.float32(-128), np.uint32(0x3B808081).view(np.float32), np.float32(127), np.float32(-128)
     else:
-        origin, rng, qmax, qmin = np.float32(0), np.float32(15), np.float32(15), None
-    qs = ((mx - mn) / rng).astype(np.float32)
+        origin, inv_rng, qmax, qmin = np.float32(0), np.uint32(0x3D888889).view(np.float32), np.float32(15), None
+    qs = ((mx - mn).astype(np.float32) * inv_rng).astype(np.float32)
     qs = np.maximum(qs, np.float32(1e-5))
-    qz = (origin - (mn / qs).astype(np.float32)).astype(np.float32)
+    r = (np.float32(1) / qs).astype(np.float32)
+    qz = _fma32(-mn, r, np.broadcast_to(origin, mn.shape))
     qz = np.minimum(qz, qmax)
     if qmin is not None:
         qz = np.maximum(qz, qmin)
     qz = np.rint(qz).astype(np.float32)
-    t = (qz[..., None] + (x / qs[..., None]).astype(np.float32)).astype(np.float32)
+    t = _fma32(x, r[..., None], np.broadcast_to(qz[..., None], x.shape))
     t = np.minimum(t, qmax)
     if qmin is not None:
         t = np.maximum(t, qmin)
@@ -55,7 +76,7 @@ def quant_rows(x, mode):
     if mode == QUANT_I8:
         q = t.astype(np.int8)
     else:
-        q = np.maximum(t, 0).astype(np.uint8)  # cvt.rzi.u32.f32 saturates negatives to 0
+        q = np.maximum(t, 0).astype(np.uint8)  # cvt.rni.u32.f32 saturates negatives to 0
     return q, qz, qs
 
 
