@@ -50,6 +50,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// ---- optional timeline instrumentation (-DB2_TRACE): globaltimer stamps into a per-translation-unit buffer
+#ifdef B2_TRACE
+#define B2_TRACE_DECL(name) static __device__ unsigned long long name[32];
+#define B2_TR(name, ev) do { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); name[ev] = t_; } while (0)
+#else
+#define B2_TRACE_DECL(name)
+#define B2_TR(name, ev) do {} while (0)
+#endif
+
 // ---- programmatic dependent launch
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

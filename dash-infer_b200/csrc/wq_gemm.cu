@@ -134,6 +134,11 @@ __device__ __forceinline__ void tile_mma(float (&acc)[MT][4], uint32_t wtile, ui
   }
 }
 
+B2_TRACE_DECL(g_gemv_tr)
+#ifdef B2_TRACE
+extern "C" int b2_debug_trace_gemv(unsigned long long* host_out) { return (int)cudaMemcpyFromSymbol(host_out, g_gemv_tr, sizeof(g_gemv_tr)); }
+#endif
+
 template <int WBITS, int MT, bool GROUPED>
 __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
   using T = WTraits<WBITS>;
@@ -164,6 +169,8 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
   uint64_t* empty = full + NST;
   __shared__ int s_is_last;
 
+  const bool tr0 = blockIdx.x == 0 && tid == 0;
+  if (tr0) B2_TR(g_gemv_tr, 0);
   if (tid == 0) {
     for (int i = 0; i < NST; ++i) {
       mbar_init(&full[i], 1);
@@ -173,6 +180,7 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
   }
   __syncthreads();
   pdl_launch_dependents();  // let the next kernel start streaming ITS weights as soon as SM resources free up
+  if (tr0) B2_TR(g_gemv_tr, 1);
 
   if (warp == kWarps) {
     // ===================== producer: TMA bulk copies, independent of the previous kernel ==========
@@ -186,6 +194,7 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
         const uint32_t bytes = tiles * T::TILE_BYTES;
         mbar_arrive_expect_tx(&full[slot], bytes);
         bulk_g2s(ring + slot * T::STAGE_BYTES, wsrc + (size_t)i * T::STAGE_BYTES, bytes, &full[slot]);
+        if (blockIdx.x == 0 && i == 0) B2_TR(g_gemv_tr, 2);
       }
     }
     return;
@@ -206,6 +215,7 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
     for (int c = 0; c < 4; ++c) acc[m][c] = facc[m][c] = 0.f;
 
   pdl_wait();  // activations / workspace / counters belong to the previous kernels from here on
+  if (tr0) B2_TR(g_gemv_tr, 3);
 
   if (p.norm_sumsq) {  // LayerNormNoBeta statistics from the producer's per-tile partial sums (fixed order)
     for (int m = warp; m < MP; m += kWarps) {
@@ -270,12 +280,14 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
       }
     }
     named_bar_sync(1, kWarps * 32);
+    if (tr0 && xc0 == 0) B2_TR(g_gemv_tr, 4);
 
     // ---- main loop: one pipeline stage (TPS k-tiles) per iteration
     int gcount = 0;  // tiles into the current quant group
     for (int xs0 = 0; xs0 < xn; xs0 += T::TPS, ++stage_i) {
       const int slot = stage_i & (NST - 1);
       mbar_wait(&full[slot], (stage_i >> p.nst_log2) & 1);
+      if (tr0 && stage_i == 0) B2_TR(g_gemv_tr, 5);
       const uint32_t wst = w_ring + slot * T::STAGE_BYTES;
 #pragma unroll
       for (int ti = 0; ti < T::TPS; ++ti) {
@@ -306,6 +318,7 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
     }
   }
 
+  if (tr0) B2_TR(g_gemv_tr, 6);
   // ---- dequant epilogue on the accumulators (per-channel) and park the tile in shared memory
 #pragma unroll
   for (int m = 0; m < MT; ++m) {
@@ -332,13 +345,16 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
       *reinterpret_cast<float4*>(wsu + i) = *reinterpret_cast<const float4*>(fs + i);
     __threadfence();
     named_bar_sync(1, kWarps * 32);
+    if (tr0) B2_TR(g_gemv_tr, 7);
     if (ctid == 0) {
       const unsigned prev = atomicAdd(&p.counters[ng], 1u);
       s_is_last = (prev == (unsigned)(p.S - 1));
     }
     named_bar_sync(1, kWarps * 32);
+    if (tr0) B2_TR(g_gemv_tr, 8);
     if (!s_is_last) return;
     __threadfence();
+    if (ng == 0 && ctid == 0) B2_TR(g_gemv_tr, 9);
     // fixed-order sum over the S partials (deterministic); loads are issued 8 at a time so the L2 round
     // trips overlap instead of serialising behind the adds
     const float* wsg = p.ws + (size_t)ng * p.S * MPK;
@@ -357,6 +373,7 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
     }
     if (ctid == 0) p.counters[ng] = 0;  // re-arm for the next launch / graph replay
     named_bar_sync(1, kWarps * 32);
+    if (ng == 0 && ctid == 0) B2_TR(g_gemv_tr, 10);
   }
 
   // ---- final: alpha, bias, activation, residual, bf16 store (coalesced along n)
@@ -476,6 +493,7 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
       fs[m * kBN + np * 2 + 1] = has1 ? __bfloat162float(__float2bfloat16(v1)) : 0.f;
     }
   }
+  if (ng == 0 && ctid == 0) B2_TR(g_gemv_tr, 11);
   if (p.sumsq_out) {  // per-tile sum of squares of the output rows, for the next op's fused RMSNorm
     named_bar_sync(1, kWarps * 32);
     for (int m = warp; m < p.M; m += kWarps) {

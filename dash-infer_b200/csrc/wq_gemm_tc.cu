@@ -54,44 +54,6 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// cta_group::2: one commit arrives on the barrier at the same shared-memory offset in BOTH CTAs of the pair
-__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "h"((uint16_t)3)
-               : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// address of the same shared-memory location in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
-}
 __device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
                "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
@@ -106,16 +68,6 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
-      : "memory");
-}
-// cta_group::2: D[256 x N] over the TMEM of both CTAs (+)= A[256 x 16] (128 rows in each CTA's TMEM) * B[16 x N] (N/2 columns in
-// each CTA's shared memory, same offset); issued by the leader CTA only
-__device__ __forceinline__ void tc_mma_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
       : "memory");
 }
 // D[tmem] (+)= A[tmem] * B[smem desc]
@@ -171,13 +123,8 @@ struct TcParams {
 #define TC_ABL(bit) false
 #endif
 
-// MULTI: a CTA walks several units (more units than SMs); the single-unit instantiation folds the unit loop away.
-// CG = 2: CTA PAIRS (clusters of two, tcgen05 cta_group::2).  The pair owns two adjacent 128-channel n-groups and the same
-// k-range; each CTA streams and dequantizes ITS n-group into its own TMEM and loads HALF of the batch rows (32 of the 64
-// MMA columns) into its shared memory; the leader (cluster rank 0) issues one M=256 MMA per k16 step for both.  Per SM
-// that is half the MMA issue slots and half the activation shared-memory traffic of CG = 1: at batch 64 the tensor pipe
-// (45..61 clocks per 128x64x16 MMA) no longer runs behind the 44 clocks per MMA the HBM stream allows.
-template <int WBITS, bool MULTI, int CG>
+// MULTI: a CTA walks several units (more units than SMs); the single-unit instantiation folds the unit loop away
+template <int WBITS, bool MULTI>
 __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap amap) {
   constexpr int TILE_BYTES = WBITS == 4 ? 4096 : (WBITS == 8 ? 8192 : 16384);
   constexpr int NCH = WBITS == 4 ? 2 : (WBITS == 8 ? 4 : 8);  // 16B chunks per row per k-tile
@@ -189,9 +136,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
   constexpr int ABUF = ACOLS * TPS;            // per stage (128 columns)
   constexpr int NAB = kTcNSX;                  // A stages in TMEM == activation stages (one 'ready' barrier per stage)
   constexpr int WSTAGE = TPS * TILE_BYTES;     // 16 KB
-  constexpr int NML = kTcNM / CG;              // batch rows whose activations THIS CTA loads (the MMA sees all kTcNM)
-  constexpr int XTILE = NML * 128;             // bytes per k-tile of activations in this CTA
-  constexpr int XSTAGE = TPS * XTILE;          // 32 KB / 16 KB (half of it per CTA of a pair)
+  constexpr int XSTAGE = TPS * kTcXTile;       // 32 KB / 16 KB
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* xring = smem;                                   // NSX x XSTAGE, 1024B aligned (SWIZZLE_128B atoms)
@@ -205,41 +150,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
   uint64_t* afull = xsum + kTcNSX;        // [NAB] stage ready: activation TMA tx + 4 dequant-warp arrivals (A stage in TMEM)
   uint64_t* mdone = afull + NAB;          // [NSX] tensor core done with stage (tcgen05.commit): frees A buffer + X slot
   uint64_t* dfull = mdone + kTcNSX;
-  uint64_t* pfull = dfull + 1;            // [NAB] (CG = 2, leader): both CTAs' stage ready (2 forwarded arrivals)
-  uint64_t* sumbar = pfull + NAB;         // (CG = 2) all kTcNM row sums present: 32 local + 32 remote lane arrivals
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sumbar + 1);
-  float* suma_part = reinterpret_cast<float*>(tmem_slot + 2);  // [32] (CG = 2) odd-tile partial row sums of warp 7
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dfull + 1);
   __shared__ int s_is_last;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) { TC_GT(0); TC_TRACE(7, 5); }
-  const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;   // 0 = leader
-  // work units: CG = 1 (n-group, k-split); CG = 2 (PAIR of n-groups, k-split), walked by clusters
-  const int nunits = (p.NG / CG) * p.S;
-  const int wid = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;     // walker index (CTA or cluster)
-  const int nwalk = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int nunits = p.NG * p.S;
 
   if (tid == 0) {
     for (int i = 0; i < NSW; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wfree[i], 4); }
     // afull = stage ready: activation TMA tx + 4 dequant-warp arrivals (the MMA thread and the row-sum warps wait on it)
     for (int i = 0; i < kTcNSX; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xsum[i], 2); mbar_init(&mdone[i], 1); mbar_init(&afull[i], 5); }
     mbar_init(dfull, 1);
-    for (int i = 0; i < NAB; ++i) mbar_init(&pfull[i], 2);
-    mbar_init(sumbar, 64);
     fence_mbar_init();
   }
-  if (warp == 1) {  // TMEM allocation (this warp also frees it); a pair allocates the same columns in both CTAs
-    if (CG == 1) {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTcTmemCols) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    } else {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTcTmemCols) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
+  if (warp == 1) {  // TMEM allocation (this warp also frees it)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTcTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  if (CG == 2) cluster_sync_all();  // the peer's barriers must be initialised before any remote arrive / multicast commit
-  else __syncthreads();
+  __syncthreads();
   tc_fence_after();
   // warp-uniform for the compiler: tcgen05 operands then live in uniform registers (otherwise every tcgen05.mma is
   // wrapped in an ELECT / R2UR.BROADCAST waterfall loop, ~70 clocks per MMA instead of the 45-clock hardware floor)
@@ -253,12 +183,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
   // the A buffer is free).
   int w_pre = 0;  // weight stages of the current unit already issued during the previous unit's tail (producer thread only)
   // (loop control and everything the tcgen05.mma operands derive from must stay provably warp-uniform: see `tmem`)
-  const int my_units = !MULTI ? 1 : (wid < nunits) ? (nunits - wid + nwalk - 1) / nwalk : 0;
+  const int my_units = !MULTI ? 1 : ((int)blockIdx.x < nunits) ? (nunits - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   for (int uit = 0; uit < my_units; ++uit) {
-  const int unit = wid + uit * nwalk;
-  const int ngu = unit / p.S;
-  const int ng = CG == 2 ? 2 * ngu + (int)crank : ngu;   // this CTA's n-group
-  const int s = unit - ngu * p.S;
+  const int unit = (int)blockIdx.x + uit * (int)gridDim.x;
+  const int ng = unit / p.S;
+  const int s = unit - ng * p.S;
   const int kt0 = (int)((int64_t)s * p.KT / p.S), kt1 = (int)((int64_t)(s + 1) * p.KT / p.S);
   const int nt = kt1 - kt0;
   const int nst = (nt + TPS - 1) / TPS;  // pipeline stages of this unit
@@ -282,10 +211,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
       }
       // head of the next unit: its first stages stream in while this unit drains and runs its epilogue
       w_pre = 0;
-      const int nu = unit + nwalk;
+      const int nu = unit + gridDim.x;
       if (MULTI && nu < nunits) {
-        const int ngu2 = nu / p.S, s2 = nu - ngu2 * p.S;
-        const int ng2 = CG == 2 ? 2 * ngu2 + (int)crank : ngu2;
+        const int ng2 = nu / p.S, s2 = nu - ng2 * p.S;
         const int k0 = (int)((int64_t)s2 * p.KT / p.S), k1 = (int)((int64_t)(s2 + 1) * p.KT / p.S);
         const int nt2 = k1 - k0, nst2 = (nt2 + TPS - 1) / TPS;
         const uint8_t* wsrc2 = p.packed + ((size_t)ng2 * p.KT + k0) * TILE_BYTES;
@@ -311,11 +239,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
         // the loads complete on the stage's 'ready' barrier (what the MMA thread waits for, together with the dequant
         // arrivals); the row-sum warps wait on the same barrier phase
         if (TC_ABL(8)) { mbar_arrive(&afull[slot]); continue; }
-        mbar_arrive_expect_tx(&afull[slot], tiles * XTILE);
-        for (int ti = 0; ti < tiles; ++ti)   // a pair: this CTA's half of the batch rows (box = 64 k x NML rows)
+        mbar_arrive_expect_tx(&afull[slot], tiles * kTcXTile);
+        for (int ti = 0; ti < tiles; ++ti)
           asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                       ::"r"(smem_u32(xring + slot * XSTAGE + ti * XTILE)), "l"(reinterpret_cast<uint64_t>(&amap)),
-                         "r"((kt0 + st * TPS + ti) * kBK), "r"((int)crank * NML), "r"(smem_u32(&afull[slot]))
+                       ::"r"(smem_u32(xring + slot * XSTAGE + ti * kTcXTile)), "l"(reinterpret_cast<uint64_t>(&amap)),
+                         "r"((kt0 + st * TPS + ti) * kBK), "r"(0), "r"(smem_u32(&afull[slot]))
                        : "memory");
       }
     }
@@ -325,25 +253,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
     // compiler, and a non-uniform operand costs an R2UR waterfall per MMA (see `tmem`)
     const int gb = __shfl_sync(0xffffffffu, gbase, 0);
     const int nst_u = __shfl_sync(0xffffffffu, nst, 0), nt_u = __shfl_sync(0xffffffffu, nt, 0);
-    if (lane == 0 && crank == 0) {
-      // instruction descriptor: D=f32, A=B=bf16, both K-major, N = NM, M = 128 per CTA (cute::UMMA::InstrDescriptor)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcNM >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N = NM, M = 128 (cute::UMMA::InstrDescriptor)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcNM >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       // B smem descriptor (cute::UMMA::SmemDescriptor): K-major, SWIZZLE_128B, SBO = 1024 B (8-row groups), version 1
       const uint64_t desc_hi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
       const uint32_t xbase = smem_u32(xring);
       for (int st = 0; st < nst_u; ++st) {
         const int g = gb + st;
         const int ab = g % NAB, xs = g % kTcNSX;
-        // dequantized A stored in TMEM and activations landed (CG = 2: in BOTH CTAs, forwarded by their row-sum warps)
-        if (CG == 2) mbar_wait_cluster(&pfull[ab], (g / NAB) & 1);
-        else mbar_wait(&afull[ab], (g / NAB) & 1);
+        mbar_wait(&afull[ab], (g / NAB) & 1);  // dequantized A stored in TMEM and activations landed
         tc_fence_after();
         TC_TRACE(1, g);
         const int tiles = min(TPS, nt_u - st * TPS);
 #pragma unroll
         for (int ti = 0; ti < TPS; ++ti) {
           if (ti < tiles) {
-            const uint32_t xaddr = xbase + xs * XSTAGE + ti * XTILE;
+            const uint32_t xaddr = xbase + xs * XSTAGE + ti * kTcXTile;
             // start-address field is (addr >> 4): a k16 step (32 B) inside the swizzle atom is +2
             const uint64_t bdesc0 = desc_hi | (uint64_t)(((xaddr >> 4) & 0x3FFF) | (1u << 16));
 #pragma unroll
@@ -353,44 +279,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
               if (ti * 4 + kk == TPS * 4 - 1) TC_TRACE(15, g);
               if (TC_ABL(4)) continue;
               if (WBITS != 8) {
-                if (CG == 2) tc_mma_ts_pair(tmem + kTcColsD, tmem + kTcColsA + ab * ABUF + ti * ACOLS + kk * 8, bdesc, idesc, acc);
-                else tc_mma_ts(tmem + kTcColsD, tmem + kTcColsA + ab * ABUF + ti * ACOLS + kk * 8, bdesc, idesc, acc);
-              } else if (CG == 2) {  // W8: per k16 step the buffer holds [lo plane | hi plane], 8 columns each
-                tc_mma_ts_pair(tmem + kTcColsD, tmem + kTcColsA + ab * ABUF + ti * ACOLS + kk * 16, bdesc, idesc, acc);
-                tc_mma_ts_pair(tmem + kTcColsD, tmem + kTcColsA + ab * ABUF + ti * ACOLS + kk * 16 + 8, bdesc, idesc, 1u);
-              } else {
+                tc_mma_ts(tmem + kTcColsD, tmem + kTcColsA + ab * ABUF + ti * ACOLS + kk * 8, bdesc, idesc, acc);
+              } else {  // W8: per k16 step the buffer holds [lo plane | hi plane], 8 columns each
                 tc_mma_ts(tmem + kTcColsD, tmem + kTcColsA + ab * ABUF + ti * ACOLS + kk * 16, bdesc, idesc, acc);
                 tc_mma_ts(tmem + kTcColsD, tmem + kTcColsA + ab * ABUF + ti * ACOLS + kk * 16 + 8, bdesc, idesc, 1u);
               }
             }
           }
         }
-        if (CG == 2) {  // the stage / the accumulator are released in both CTAs
-          tc_commit_pair(&mdone[xs]);
-          if (st == nst_u - 1) tc_commit_pair(dfull);
-        } else {
-          tc_commit(&mdone[xs]);
-          if (st == nst_u - 1) tc_commit(dfull);
-        }
+        tc_commit(&mdone[xs]);
+        if (st == nst_u - 1) tc_commit(dfull);
         TC_TRACE(2, g);
       }
     }
   } else if (warp == 6 || warp == 7) {
-    // ===================== row sums of the landed activation tiles =====================
-    // CG = 1: thread = one of the 64 batch rows.  CG = 2: this CTA holds 32 rows; warp 6 takes the even k-tiles of a stage,
-    // warp 7 the odd ones (row = lane), and warp 6 lane 0 forwards "this CTA's stage is ready" to the leader's pair barrier.
-    const int xt = CG == 2 ? lane : tid - 192;
-    const int ti0 = CG == 2 ? warp - 6 : 0, tstep = CG == 2 ? 2 : 1;
+    // ===================== row sums of the landed activation tiles (row = xt) =====================
+    const int xt = tid - 192;  // 0..63
     float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
-    const uint32_t pfull_leader = CG == 2 ? mapa_u32(smem_u32(pfull), 0u) : 0u;
     for (int st = 0; st < nst; ++st) {
       const int g = gbase + st;
       const int slot = g % kTcNSX;
       mbar_wait(&afull[slot], (g / kTcNSX) & 1);  // stage ready (implies its activation tiles landed)
-      if (CG == 2 && warp == 6 && lane == 0) mbar_arrive_cluster(pfull_leader + slot * 8);
       const int tiles = (TC_ABL(1) || WBITS == 16) ? 0 : min(TPS, nt - st * TPS);  // bf16 weights: no zero-point term
-      for (int ti = ti0; ti < tiles; ti += tstep) {
-        const uint32_t rbase = smem_u32(xring + slot * XSTAGE + ti * XTILE) + xt * 128;
+      for (int ti = 0; ti < tiles; ++ti) {
+        const uint32_t rbase = smem_u32(xring + slot * XSTAGE + ti * kTcXTile) + xt * 128;
 #pragma unroll
         for (int c = 0; c < 8; c += 2) {
           const uint4 v = lds128(rbase + ((c ^ (xt & 7)) << 4));
@@ -405,24 +317,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
       if (lane == 0) mbar_arrive(&xsum[slot]);
       if (xt == 0) TC_TRACE(3, g);
     }
-    if (CG == 1) {
-      suma[xt] = (r0 + r1) + (r2 + r3);
-      asm volatile("bar.sync 3, 320;" ::: "memory");  // hand the sums to the dequant/epilogue warps
-    } else {
-      // both CTAs need all 64 sums (each epilogue covers every batch row of its own channels): this CTA's 32 go to its own
-      // suma[] and, through distributed shared memory, to the peer's; each writing lane then arrives on both sum barriers
-      if (warp == 7) suma_part[lane] = (r0 + r1) + (r2 + r3);
-      asm volatile("bar.sync 4, 64;" ::: "memory");
-      if (warp == 6) {
-        const float tot = ((r0 + r1) + (r2 + r3)) + suma_part[lane];
-        const int idx = (int)crank * NML + lane;
-        suma[idx] = tot;
-        st_cluster_f32(mapa_u32(smem_u32(suma + idx), crank ^ 1u), tot);
-        mbar_arrive_cluster(mapa_u32(smem_u32(sumbar), crank));
-        mbar_arrive_cluster(mapa_u32(smem_u32(sumbar), crank ^ 1u));
-      }
-      asm volatile("bar.sync 4, 64;" ::: "memory");  // suma_part is rewritten by the next unit
-    }
+    suma[xt] = (r0 + r1) + (r2 + r3);
+    asm volatile("bar.sync 3, 320;" ::: "memory");  // hand the sums to the dequant/epilogue warps
   } else {
     // ===================== dequant (warps 2..5: even stages, warps 9..12: odd stages), then TMEM -> smem =====================
     const int grp = warp >= 9 ? 1 : 0;
@@ -515,8 +411,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
     mbar_wait(dfull, uit & 1);
     if (tracer) TC_TRACE(7, 0);
     tc_fence_after();
-    if (CG == 2) mbar_wait_cluster(sumbar, uit & 1);               // all 64 row sums (32 of them from the peer CTA)
-    else asm volatile("bar.sync 3, 320;" ::: "memory");            // row sums ready
+    asm volatile("bar.sync 3, 320;" ::: "memory");  // row sums ready
     if (grp * 32 < p.M) {
       uint32_t d[32];
       tc_ld32(trow + kTcColsD + grp * 32, d);
@@ -681,18 +576,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
 
   tc_fence_before();
   if (MULTI) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy tile writes before the next unit's TMA writes
-  // the tile in the X ring and the accumulator are free again; a pair meets here as a whole: the leader's next MMAs write the
-  // peer's accumulator and read the peer's activation ring, and neither CTA may exit while the other can still reach it
-  if (CG == 2) cluster_sync_all();
-  else __syncthreads();
+  __syncthreads();  // the tile in the X ring and the accumulator are free again
   tc_fence_after();
   }  // unit loop
 
   if (tid == 0) { TC_TRACE(7, 3); TC_GT(2); }
   if (warp == 1) {
     tc_fence_after();
-    if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTcTmemCols) : "memory");
-    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTcTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTcTmemCols) : "memory");
   }
 }
 
@@ -711,15 +602,15 @@ int tc_smem_bytes(int wbits) {
   const int tps = wbits == 4 ? 4 : 2;
   const int wstage = tps * (wbits == 4 ? 4096 : (wbits == 8 ? 8192 : 16384));
   const int nsw = wbits == 16 ? 4 : kTcNSW;
-  return 1024 + kTcNSX * tps * kTcXTile + nsw * wstage + kTcNM * 4 + 64 * 8 + 64;  // (a pair uses half of the X ring)
+  return 1024 + kTcNSX * tps * kTcXTile + nsw * wstage + kTcNM * 4 + 48 * 8 + 64;
 }
 
 cudaError_t tc_configure(int wbits) {
   cudaError_t e = cudaSuccess;
   auto cfg = [&](auto kern) { if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(wbits)); };
-  if (wbits == 4) { cfg(wq_gemm_tc_kernel<4, false, 1>); cfg(wq_gemm_tc_kernel<4, true, 1>); cfg(wq_gemm_tc_kernel<4, false, 2>); cfg(wq_gemm_tc_kernel<4, true, 2>); }
-  else if (wbits == 16) { cfg(wq_gemm_tc_kernel<16, false, 1>); cfg(wq_gemm_tc_kernel<16, true, 1>); cfg(wq_gemm_tc_kernel<16, false, 2>); cfg(wq_gemm_tc_kernel<16, true, 2>); }
-  else { cfg(wq_gemm_tc_kernel<8, false, 1>); cfg(wq_gemm_tc_kernel<8, true, 1>); cfg(wq_gemm_tc_kernel<8, false, 2>); cfg(wq_gemm_tc_kernel<8, true, 2>); }
+  if (wbits == 4) { cfg(wq_gemm_tc_kernel<4, false>); cfg(wq_gemm_tc_kernel<4, true>); }
+  else if (wbits == 16) { cfg(wq_gemm_tc_kernel<16, false>); cfg(wq_gemm_tc_kernel<16, true>); }
+  else { cfg(wq_gemm_tc_kernel<8, false>); cfg(wq_gemm_tc_kernel<8, true>); }
   return e;
 }
 
@@ -738,46 +629,14 @@ static EncodeTiledFn encode_tiled() {
   return fn;
 }
 
-// launch with the PDL attribute and, for CTA pairs, a cluster dimension of 2
-template <typename... KArgs, typename... Args>
-static cudaError_t launch_tc(void (*kernel)(KArgs...), int grid, int cluster, size_t smem, cudaStream_t stream, Args... args) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kTcThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
-  int n = 0;
-  if (pdl_enabled()) {
-    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[n].val.programmaticStreamSerializationAllowed = 1;
-    ++n;
-  }
-  if (cluster > 1) {
-    attr[n].id = cudaLaunchAttributeClusterDimension;
-    attr[n].val.clusterDim.x = cluster;
-    attr[n].val.clusterDim.y = 1;
-    attr[n].val.clusterDim.z = 1;
-    ++n;
-  }
-  cfg.attrs = attr;
-  cfg.numAttrs = n;
-  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-}
-
 cudaError_t tc_launch(int wbits, const TcLaunch& a, cudaStream_t stream) {
   EncodeTiledFn enc = encode_tiled();
   if (!enc) return cudaErrorNotSupported;
-  // CTA pairs (cta_group::2) when the batch fills more than one CTA's half (M > 32) and the n-groups pair up;
-  // B2_GEMM_TC_CG=1 forces single CTAs, B2_GEMM_TC_CG_MIN_M moves the threshold
-  static const int cg_env = [] { const char* e = getenv("B2_GEMM_TC_CG"); return e ? atoi(e) : 2; }();
-  static const int cg_min_m = [] { const char* e = getenv("B2_GEMM_TC_CG_MIN_M"); return e ? atoi(e) : 33; }();
-  const int cg = (cg_env == 2 && a.M >= cg_min_m && (a.NG % 2) == 0) ? 2 : 1;
-  // activations A[M, K] bf16, row stride lda: box = 64 k x (64 / cg) rows, 128B swizzle, zero fill outside [M, K]
+  // activations A[M, K] bf16, row stride lda: box = 64 k x 64 rows, 128B swizzle, zero fill outside [M, K]
   alignas(64) CUtensorMap amap;
   const cuuint64_t gdim[2] = {(cuuint64_t)a.K, (cuuint64_t)a.M};
   const cuuint64_t gstride[1] = {(cuuint64_t)a.lda * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)(kTcNM / cg)};
+  const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kTcNM};
   const cuuint32_t estr[2] = {1, 1};
   if (enc(&amap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(a.A), gdim, gstride, box, estr,
           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -795,23 +654,20 @@ cudaError_t tc_launch(int wbits, const TcLaunch& a, cudaStream_t stream) {
 #ifdef B2_TC_TRACE
   p.dbg = (int)(g_tc_host_launches++);  // launch id (frozen into a captured graph node)
 #endif
-  // persistent: one CTA (or pair) per SM (pair of SMs) walks the units; B2_GEMM_TC_PERSIST=0 launches one walker per unit
+  // persistent: one CTA per SM walks the (n-group, k-split) units; B2_GEMM_TC_PERSIST=0 launches one CTA per unit
   static const int persist = [] { const char* e = getenv("B2_GEMM_TC_PERSIST"); return e ? atoi(e) : 1; }();
-  const int units = (a.NG / cg) * a.S;
-  const int max_walkers = sm_count() / cg;
-  const int walkers = (persist && units > max_walkers) ? max_walkers : units;
-  const bool multi = units > walkers;
-  const int grid = walkers * cg;
+  const int units = a.NG * a.S;
+  const int grid = (persist && units > sm_count()) ? sm_count() : units;
+  const bool multi = units > grid;
   const size_t smem = (size_t)tc_smem_bytes(wbits);
-#define B2_TC_GO(W)                                                                                                        \
-  (cg == 2 ? (multi ? launch_tc(wq_gemm_tc_kernel<W, true, 2>, grid, 2, smem, stream, p, amap)                             \
-                    : launch_tc(wq_gemm_tc_kernel<W, false, 2>, grid, 2, smem, stream, p, amap))                           \
-           : (multi ? launch_tc(wq_gemm_tc_kernel<W, true, 1>, grid, 1, smem, stream, p, amap)                             \
-                    : launch_tc(wq_gemm_tc_kernel<W, false, 1>, grid, 1, smem, stream, p, amap)))
-  if (wbits == 4) return B2_TC_GO(4);
-  if (wbits == 16) return B2_TC_GO(16);
-  return B2_TC_GO(8);
-#undef B2_TC_GO
+  if (wbits == 4)
+    return multi ? launch(wq_gemm_tc_kernel<4, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap)
+                 : launch(wq_gemm_tc_kernel<4, false>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap);
+  if (wbits == 16)
+    return multi ? launch(wq_gemm_tc_kernel<16, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap)
+                 : launch(wq_gemm_tc_kernel<16, false>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap);
+  return multi ? launch(wq_gemm_tc_kernel<8, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap)
+               : launch(wq_gemm_tc_kernel<8, false>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap);
 }
 
 }  // namespace b2

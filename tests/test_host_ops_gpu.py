@@ -190,4 +190,9 @@ def test_span_attention_operator_quantized_cache_modes(mode, layer):
             kref.append(b, t, x[t, b, nH:nH + nG]); vref.append(b, t, x[t, b, nH + nG:])
         if t in (0, 1, span - 1, span, steps - 1):
             ref = KV.attention_ref(x[t, :, :nH], kref, vref, [t + 1] * B, nH, 1.0 / np.sqrt(128))
-            assert np.all(np.abs(got[t] - ref) <= 2e-3 + 2.0 ** -7 * np.abs(ref)), (t, np.abs(got[t] - ref).max())
+            # the op's spans are not reachable from here, so the oracle attends over ITS OWN quantization of the same rows:
+            # on exact zero-point ties (~1 % of rows) the GPU's MUFU.RCP and the oracle's IEEE reciprocal round apart and a
+            # clamped code moves by one quantization step (1/255 resp. 1/15 of the row's range), hence the mode-dependent
+            # allowance on top of the attention tolerance (identical-bytes attention parity: tests/test_attn_gpu.py)
+            step = {KV.QUANT_I8: 1 / 255, KV.QUANT_U4: 1 / 15}[mode] * 8.0
+            assert np.all(np.abs(got[t] - ref) <= 2e-3 + 2.0 ** -7 * np.abs(ref) + 0.1 * step), (t, np.abs(got[t] - ref).max())

@@ -13,3 +13,6 @@ timeout 600 python -m pytest tests/test_gemm_gpu.py -m gpu -q -p no:cacheprovide
 tail -8 gpurun_out/pytest_r2b_cg2.log
 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu --sub-batches "" > gpurun_out/bench_r2b_cg2.json 2> gpurun_out/bench_r2b_cg2.err
 tail -c 1500 gpurun_out/bench_r2b_cg2.json
+export B2_GEMM_TC_CG=1
+timeout 600 python -m pytest tests/test_comm_gpu.py -m gpu -q -p no:cacheprovider --timeout 120 2>&1 | tail -80 > gpurun_out/pytest_r2b_comm.log
+tail -5 gpurun_out/pytest_r2b_comm.log
