@@ -969,6 +969,32 @@ static int run_impl(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, int64_t
     }
     return B2_OK;
   }
+  // ---- batches <= 32 without global split-K (wq_gemv2.cu) unless a fusion only the split-K kernel implements is asked for
+  if (!fused && !comm) {
+    for (int m0 = 0; m0 < M; m0 += 32) {
+      Gemv2Launch a;
+      a.packed = (const uint8_t*)h->packed; a.sz = h->sz;
+      a.A = (const __nv_bfloat16*)A + (int64_t)m0 * lda; a.lda = lda;
+      a.C = (__nv_bfloat16*)C + (int64_t)m0 * ldc; a.ldc = ldc;
+      a.bias = (const __nv_bfloat16*)bias;
+      a.residual = residual ? (const __nv_bfloat16*)residual + (int64_t)m0 * ldc : nullptr;
+      a.M = (M - m0) > 32 ? 32 : (M - m0);
+      a.N = h->d.N; a.K = h->d.K; a.Np = h->Np; a.KT = h->KT; a.NG = h->NG;
+      a.wbits = h->d.wbits; a.group_tiles = h->group_tiles; a.pair = h->pair; a.act = activation; a.alpha = alpha;
+      Gemv2Plan pl;
+      if (!gemv2_plan(a, &pl)) {
+        if (m0 == 0) goto splitk;  // nothing launched yet: the whole call takes the split-K kernel
+        return B2_ERR_INTERNAL;
+      }
+      cudaError_t e = gemv2_launch(a, pl, stream);
+      if (e != cudaSuccess) {
+        set_last_error("wq_gemv2 launch", e);
+        return B2_ERR_CUDA;
+      }
+    }
+    return B2_OK;
+  }
+splitk:
   const int rpl = rows_per_launch(h);
   for (int m0 = 0; m0 < M; m0 += rpl) {
     const int mc = (M - m0) > rpl ? rpl : (M - m0);

@@ -36,6 +36,28 @@ struct TcLaunch {
   int act;
   float alpha;
 };
+// GEMV without global split-K (wq_gemv2.cu)
+struct Gemv2Launch {
+  const uint8_t* packed;
+  const float2* sz;
+  const __nv_bfloat16* A;
+  int64_t lda;
+  __nv_bfloat16* C;
+  int64_t ldc;
+  const __nv_bfloat16* bias;
+  const __nv_bfloat16* residual;
+  int M, N, K, Np, KT, NG;
+  int wbits, group_tiles;  // group_tiles: k-tiles per quantization group, 0 = per channel
+  bool pair;
+  int act;
+  float alpha;
+};
+struct Gemv2Plan {
+  int cb_log2, q, xt, nst_log2, mt, grid, smem;
+};
+bool gemv2_plan(const Gemv2Launch& a, Gemv2Plan* plan);   // false: use the split-K kernel
+cudaError_t gemv2_launch(const Gemv2Launch& a, const Gemv2Plan& plan, cudaStream_t stream);
+
 constexpr int kTcMaxM = 64;  // batch rows per tcgen05 launch
 int tc_smem_bytes(int wbits);
 cudaError_t tc_configure(int wbits);

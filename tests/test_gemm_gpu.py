@@ -121,6 +121,7 @@ def test_tcgen05_persistent_units():
 
 
 def test_forced_split_paths(monkeypatch):
+    monkeypatch.setenv("B2_GEMV2", "0")  # the split-K kernel (still used for fused norm / all-reduce epilogues and tiny N)
     monkeypatch.setenv("B2_GEMM_FORCE_SPLIT", "1")
     _run(4, 1024, 256, 2, -1, seed=51)
     monkeypatch.setenv("B2_GEMM_FORCE_SPLIT", "7")
@@ -311,3 +312,42 @@ def test_mixed_group_sizes_share_a_kernel():
             torch.cuda.synchronize()
             ref = Q.gemm_wq_math(a.float().numpy(), qu, s.float().numpy(), z.float().numpy(), group)
             assert Q.err_min_abs_rel(ref, out.float().cpu().numpy()) <= TOL
+
+
+@pytest.mark.parametrize("cb", [16, 32, 64, 128])
+def test_gemv2_every_channel_block(monkeypatch, cb):
+    """The no-split-K GEMV with its channel block forced to 16 / 32 / 64 / 128 (8 / 4 / 2 / 1 k-slices per CTA): per-channel
+    and sub-channel weights, int4 / int8 / bf16, ragged N and K, bias / activation / residual, and the gate/up pair image
+    (needs >= 32: 16 gate + 16 up rows per CTA)."""
+    monkeypatch.setenv("B2_GEMV2", "2")  # every shape (the default policy takes dense bf16 weights only)
+    monkeypatch.setenv("B2_GEMV2_CB", str(cb))
+    _run(4, 1024, 640, 1, -1, seed=1, use_bias=True, use_res=True)
+    _run(4, 520, 130, 3, -1, seed=2)                       # K % 64 != 0, ragged N
+    _run(8, 1024, 384, 8, -1, seed=3, act=5)
+    _run(16, 512, 256, 16, -1, seed=4, use_bias=True)
+    _run(4, 1024, 384, 5, 128, seed=5)                     # sub-channel: one group per warp quantum
+    _run(8, 1024, 384, 16, 256, seed=6, use_res=True)
+    _run(4, 1152, 256, 32, 128, seed=7)                    # sub-channel at M = 32: one pass (MT = 4), 9 groups
+    if cb >= 32:
+        _pair_case(4, 1024, 704, 1, -1, seed=8)
+        _pair_case(8, 1024, 704, 16, -1, seed=9)
+        _pair_case(4, 1024, 704, 8, 128, seed=10)
+
+
+def test_gemv2_matches_split_k_kernel(monkeypatch):
+    """Both decompositions stream the same image: results agree to fp32 summation order (then one bf16 rounding)."""
+    from b200spark import ops, quantize as PQ
+    K, N, M = 3584, 4608, 8
+    g = torch.Generator().manual_seed(12)
+    w = (torch.randn(K, N, generator=g) * 0.02).to(torch.bfloat16)
+    a = (torch.rand(M, K, generator=g) * 2 - 1).to(torch.bfloat16).cuda()
+    q, s, z = PQ.quantize_a16w4(w, -1)
+    op = ops.GemmWQ(K, N, 4, -1, max_m=M).prepare(q.cuda(), s.cuda(), z.cuda())
+    ws = ops.Workspace()
+    monkeypatch.setenv("B2_GEMV2", "2")
+    y2 = op(a, ws).float()
+    monkeypatch.setenv("B2_GEMV2", "0")
+    y1 = op(a, ws).float()
+    torch.cuda.synchronize()
+    assert (y1 - y2).abs().max().item() <= 2.0 ** -7 * y1.abs().max().item()
+    assert (y1 != y2).float().mean().item() < 0.02
