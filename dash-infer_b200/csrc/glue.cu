@@ -41,6 +41,111 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(__nv_bfloat16* __restrict_
   }
 }
 
+// ---- fp8 activations for the tcgen05 kind::f8f6f4 GEMM (b2_gemm_wq_run_fp8): per-token dynamic scale
+//   scale[r] = max(|x[r,:]|, tiny) / 448 ;  y = e4m3(x / scale) (round to nearest even, saturating)
+// optional fused RMSNorm (gamma != NULL): x is first normalised exactly like rmsnorm_kernel (result rounded to bf16).
+// Layout of y ("b2 fp8 activation layout"): inside every aligned group of 8 k the bytes hold k = (0,2,4,6,1,3,5,7) — the
+// order in which the int4 weight image yields its nibbles, so the GEMM's dequant needs no final byte shuffle (a dot product
+// is invariant under a common permutation of k).  tile_sums[r][kt] = sum of the QUANTIZED values of k-tile kt (64 k), the
+// zero-point term of the affine dequantisation (exact in fp32: multiples of 2^-9 below 2^15).
+__global__ void __launch_bounds__(256) quant_fp8_kernel(uint8_t* __restrict__ y, float* __restrict__ scale, float* __restrict__ tile_sums,
+                                                        const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
+                                                        int cols, int64_t ldy, int kt_count, float eps) {
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ float red[8];
+  __shared__ float red2[8];
+  const int row = blockIdx.x;
+  const __nv_bfloat16* xr = x + (size_t)row * cols;
+  float ss = 0.f, amax = 0.f;
+  for (int i = threadIdx.x * 8; i < cols; i += 256 * 8) {
+    const uint4 v = *reinterpret_cast<const uint4*>(xr + i);
+    const float f[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y), bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ss += f[j] * f[j]; amax = fmaxf(amax, fabsf(f[j])); }
+  }
+  float inv = 1.f;
+  if (gamma) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    inv = rsqrtf(tot / (float)cols + eps);
+    amax = 0.f;  // the maximum of the NORMALISED row: second pass below
+    for (int i = threadIdx.x * 8; i < cols; i += 256 * 8) {
+      const uint4 v = *reinterpret_cast<const uint4*>(xr + i);
+      const uint4 gv = *reinterpret_cast<const uint4*>(gamma + i);
+      const uint32_t vv[4] = {v.x, v.y, v.z, v.w}, gg[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t o2 = pack_bf16x2(bf16_lo(vv[j]) * inv * bf16_lo(gg[j]), bf16_hi(vv[j]) * inv * bf16_hi(gg[j]));
+        amax = fmaxf(amax, fmaxf(fabsf(bf16_lo(o2)), fabsf(bf16_hi(o2))));
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if ((threadIdx.x & 31) == 0) red2[threadIdx.x >> 5] = amax;
+  __syncthreads();
+  amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) amax = fmaxf(amax, red2[i]);
+  const float sc = fmaxf(amax, 1e-12f) / 448.f;
+  const float rs = 1.f / sc;
+  if (threadIdx.x == 0) scale[row] = sc;
+  // one thread per aligned group of 8 k; 8 consecutive threads = one 64-k tile
+  const int kend = (kt_count * 64 + 255) & ~255;  // whole warps stay in the loop (shuffles below)
+  for (int i = threadIdx.x * 8; i < kend; i += 256 * 8) {
+    float f[8];
+    if (i < cols) {
+      const uint4 v = *reinterpret_cast<const uint4*>(xr + i);
+      const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+      if (gamma) {
+        const uint4 gv = *reinterpret_cast<const uint4*>(gamma + i);
+        const uint32_t gg[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t o2 = pack_bf16x2(bf16_lo(vv[j]) * inv * bf16_lo(gg[j]), bf16_hi(vv[j]) * inv * bf16_hi(gg[j]));
+          f[2 * j] = bf16_lo(o2); f[2 * j + 1] = bf16_hi(o2);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { f[2 * j] = bf16_lo(vv[j]); f[2 * j + 1] = bf16_hi(vv[j]); }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = 0.f;
+    }
+    // e4m3 pairs: cvt packs (hi, lo) -> 16 bits; byte order (0,2,4,6,1,3,5,7)
+    uint16_t p02, p46, p13, p57;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(p02) : "f"(f[2] * rs), "f"(f[0] * rs));
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(p46) : "f"(f[6] * rs), "f"(f[4] * rs));
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(p13) : "f"(f[3] * rs), "f"(f[1] * rs));
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(p57) : "f"(f[7] * rs), "f"(f[5] * rs));
+    const uint32_t w0 = (uint32_t)p02 | ((uint32_t)p46 << 16), w1 = (uint32_t)p13 | ((uint32_t)p57 << 16);
+    if (i < cols) *reinterpret_cast<uint2*>(y + (size_t)row * ldy + i) = make_uint2(w0, w1);
+    // sum of the quantized values (decode them back: the GEMM multiplies exactly these)
+    float qs = 0.f;
+    {
+      const uint16_t pp[4] = {p02, p46, p13, p57};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t h2;
+        asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h2) : "h"(pp[j]));
+        const __half2 hh = *reinterpret_cast<const __half2*>(&h2);
+        qs += __low2float(hh) + __high2float(hh);
+      }
+    }
+    qs += __shfl_xor_sync(0xffffffffu, qs, 1);
+    qs += __shfl_xor_sync(0xffffffffu, qs, 2);
+    qs += __shfl_xor_sync(0xffffffffu, qs, 4);
+    if ((threadIdx.x & 7) == 0 && (i >> 6) < kt_count) tile_sums[(size_t)row * kt_count + (i >> 6)] = qs;
+  }
+}
+
 // in-place NeoX rotary on the q and k heads: one warp per (sequence, head)
 __global__ void __launch_bounds__(128) rotary_kernel(__nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ pos, int batch,
                                                      int n_heads, int n_groups, int rotary_dim, float log2_base) {
@@ -189,6 +294,15 @@ int b2_rmsnorm(void* y, const void* x, const void* gamma, int rows, int cols, fl
   if (cols % 8) return B2_ERR_UNSUPPORTED;
   B2_LAUNCH_CHECK("rmsnorm", launch(rmsnorm_kernel, dim3(rows), dim3(256), 0, (cudaStream_t)stream, true, (__nv_bfloat16*)y,
                                     (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma, cols, eps));
+  return B2_OK;
+}
+
+int b2_quant_fp8(void* y, int64_t ldy, float* scale, float* tile_sums, const void* x, const void* gamma, int rows, int cols,
+                 float eps, void* stream) {
+  if (!y || !scale || !tile_sums || !x || rows <= 0 || cols <= 0) return B2_ERR_PARAM;
+  if (cols % 8 || ldy < cols || (ldy & 15) || ((uintptr_t)y & 15)) return B2_ERR_UNSUPPORTED;
+  B2_LAUNCH_CHECK("quant_fp8", launch(quant_fp8_kernel, dim3(rows), dim3(256), 0, (cudaStream_t)stream, true, (uint8_t*)y, scale,
+                                      tile_sums, (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma, cols, ldy, (cols + 63) / 64, eps));
   return B2_OK;
 }
 

@@ -917,6 +917,41 @@ int b2_gemm_wq_run_fused(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, in
   return run_impl(h, A, lda, C, ldc, M, bias, residual, activation, alpha, workspace, workspace_bytes, fuse, nullptr, stream_);
 }
 
+int b2_gemm_wq_run_fp8(b2_gemm_wq_t h, const void* A8, int64_t lda_bytes, const float* a_scale, const float* tile_sums, void* C,
+                       int64_t ldc, int M, const void* bias, const void* residual, int activation, float alpha, void* workspace,
+                       size_t workspace_bytes, void* stream_) {
+  if (!h || !A8 || !a_scale || !tile_sums || !C || M <= 0) return B2_ERR_PARAM;
+  if (!h->packed) return B2_ERR_RUNTIME;
+  if (M > h->d.max_m) return B2_ERR_LIMIT;
+  if (h->d.wbits != 4 || h->group_tiles > 0) return B2_ERR_UNSUPPORTED;  // int4 per-channel weights (the IQ default)
+  if (h->pair != (activation == B2_ACT_SWIGLU)) return B2_ERR_PARAM;
+  if (activation != B2_ACT_SWIGLU && (activation < 0 || activation > B2_ACT_SIGMOID)) return B2_ERR_PARAM;
+  if (h->pair && (bias || residual)) return B2_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(A8) & 15) || (lda_bytes % 16) != 0 || lda_bytes < h->d.K) return B2_ERR_UNSUPPORTED;
+  if (int st = make_tc_plan(h)) return st;
+  const size_t need = h->tc_S <= 1 ? 16 : (size_t)h->NG * h->tc_S * kTcMaxM * kBN * sizeof(float) + 16;
+  if (workspace_bytes < need || (h->tc_S > 1 && !workspace)) return B2_ERR_PARAM;
+  for (int m0 = 0; m0 < M; m0 += kTcMaxM) {
+    TcLaunch a;
+    a.packed = (const uint8_t*)h->packed; a.sz = h->sz;
+    a.A = reinterpret_cast<const __nv_bfloat16*>((const uint8_t*)A8 + (int64_t)m0 * lda_bytes); a.lda = lda_bytes;
+    a.C = (__nv_bfloat16*)C + (int64_t)m0 * ldc; a.ldc = ldc;
+    a.bias = (const __nv_bfloat16*)bias;
+    a.residual = residual ? (const __nv_bfloat16*)residual + (int64_t)m0 * ldc : nullptr;
+    a.ws = (float*)workspace; a.counters = h->counters;
+    a.M = (M - m0) > kTcMaxM ? kTcMaxM : (M - m0);
+    a.N = h->d.N; a.K = h->d.K; a.Np = h->Np; a.KT = h->KT; a.NG = h->NG; a.S = h->tc_S;
+    a.act = activation; a.alpha = alpha;
+    a.a_scale = a_scale + m0; a.tile_sums = tile_sums + (size_t)m0 * h->KT;
+    cudaError_t e = tc_launch(4, a, (cudaStream_t)stream_);
+    if (e != cudaSuccess) {
+      set_last_error("wq_gemm_tc (fp8) launch", e);
+      return B2_ERR_CUDA;
+    }
+  }
+  return B2_OK;
+}
+
 int b2_gemm_wq_run_allreduce(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, int64_t ldc, int M, const void* bias,
                              const void* residual, float alpha, void* workspace, size_t workspace_bytes, b2_comm_t comm,
                              void* stream_) {

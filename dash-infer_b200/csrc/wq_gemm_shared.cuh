@@ -35,6 +35,8 @@ struct TcLaunch {
   int M, N, K, Np, KT, NG, S;
   int act;
   float alpha;
+  const float* a_scale = nullptr;    // != NULL: A is fp8-e4m3 in the b2 fp8 activation layout (lda in bytes)
+  const float* tile_sums = nullptr;  // [M][KT] sums of the quantized activations per 64-k tile
 };
 // GEMV without global split-K (wq_gemv2.cu)
 struct Gemv2Launch {

@@ -80,6 +80,36 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
       : "memory");
 }
 
+// fp8 (e4m3 x e4m3 -> fp32), K = 32 per instruction
+__device__ __forceinline__ void tc_mma_ts_f8(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t tc_prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+// 8 int4 codes of one image word -> 8 e4m3 bytes (exact: 0..15 are e4m3 values) in two registers:
+// P = codes of k (0,2,4,6), Q = codes of k (1,3,5,7) of the word's 8 consecutive k — the byte order of the b2 fp8 activation
+// layout (glue.cu quant_fp8_kernel).  Byte-permute look-ups: codes 0..7 from one 8-byte table, 8..15 are 0x50 | (q & 7) from a
+// second one, the choice by a sign-replicating permute of bit 3 of every nibble.  13 ALU ops per 8 weights.
+__device__ __forceinline__ void nib8_to_e4m3(uint32_t w_rot3, uint32_t& P, uint32_t& Q) {
+  const uint32_t word = __funnelshift_r(w_rot3, w_rot3, 3);  // the image stores words rotated left by 3 (bf16 path)
+  const uint32_t sel = word & 0x77777777u, selh = sel >> 16;
+  const uint32_t T0 = 0x44403800u, T1 = 0x4E4C4A48u, H0 = 0x53525150u, H1 = 0x57565554u;
+  const uint32_t plo = tc_prmt(T0, T1, sel), qlo = tc_prmt(T0, T1, selh);
+  const uint32_t phi = tc_prmt(H0, H1, sel), qhi = tc_prmt(H0, H1, selh);
+  const uint32_t ws = word << 4;
+  const uint32_t mp = tc_prmt(ws, word, 0xD9C8u), mq = tc_prmt(ws, word, 0xFBEAu);  // 0xFF where the nibble is >= 8
+  asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(P) : "r"(plo), "r"(phi), "r"(mp));   // mp ? phi : plo
+  asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(Q) : "r"(qlo), "r"(qhi), "r"(mq));
+}
+
 // optional timeline instrumentation (CTA 0 only): compiled in with -DB2_TC_TRACE
 #ifdef B2_TC_TRACE
 __device__ unsigned long long g_tc_trace[16][256];
@@ -112,6 +142,9 @@ struct TcParams {
   int M, N, K, Np, KT, NG, S;
   int act;
   float alpha;
+  // fp8 activations (A8 instantiation): per-token scale [M] and per-(row, 64-k tile) sums of the quantized values [M][KT]
+  const float* a_scale;
+  const float* tile_sums;
   int dbg;  // ablation bitmask, only honoured when compiled with -DB2_TC_ABLATE (tools/tc_ablate.py)
 };
 
@@ -124,7 +157,9 @@ struct TcParams {
 #endif
 
 // MULTI: a CTA walks several units (more units than SMs); the single-unit instantiation folds the unit loop away
-template <int WBITS, bool MULTI>
+// A8: fp8-e4m3 activations (b2_gemm_wq_run_fp8, int4 weights only): the int4 codes go to TMEM as exact e4m3 bytes, the MMAs
+// are kind::f8f6f4 with K = 32 (half the MMAs and half the TMEM stores of the bf16 path), an activation tile is 128 k wide.
+template <int WBITS, bool MULTI, bool A8 = false>
 __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap amap) {
   constexpr int TILE_BYTES = WBITS == 4 ? 4096 : (WBITS == 8 ? 8192 : 16384);
   constexpr int NCH = WBITS == 4 ? 2 : (WBITS == 8 ? 4 : 8);  // 16B chunks per row per k-tile
@@ -132,11 +167,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
   // k-tiles per pipeline stage (k256 for W4, k128 for W8): one stage = 16 KB of weights = 16 tcgen05.mma per
   // commit / barrier round trip of the issuing thread (that round trip costs ~400 clocks, an MMA 45)
   constexpr int TPS = WBITS == 4 ? 4 : 2;
-  constexpr int ACOLS = WBITS == 8 ? 64 : 32;  // TMEM columns of dequantized A per k-tile (int8: lo and hi planes)
+  static_assert(!A8 || WBITS == 4, "fp8 activations: int4 weights only");
+  constexpr int ACOLS = A8 ? 16 : (WBITS == 8 ? 64 : 32);  // TMEM columns of dequantized A per k-tile (int8: lo and hi planes)
+  constexpr int XTPS = A8 ? TPS / 2 : TPS;     // activation tiles per stage (fp8: 128 k per 128-byte row)
   constexpr int ABUF = ACOLS * TPS;            // per stage (128 columns)
   constexpr int NAB = kTcNSX;                  // A stages in TMEM == activation stages (one 'ready' barrier per stage)
   constexpr int WSTAGE = TPS * TILE_BYTES;     // 16 KB
-  constexpr int XSTAGE = TPS * kTcXTile;       // 32 KB / 16 KB
+  constexpr int XSTAGE = XTPS * kTcXTile;      // 32 KB / 16 KB
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* xring = smem;                                   // NSX x XSTAGE, 1024B aligned (SWIZZLE_128B atoms)
@@ -151,6 +188,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
   uint64_t* mdone = afull + NAB;          // [NSX] tensor core done with stage (tcgen05.commit): frees A buffer + X slot
   uint64_t* dfull = mdone + kTcNSX;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dfull + 1);
+  float* ascale = reinterpret_cast<float*>(bars) + 64;  // [NM] per-token activation scales (A8), 256 B into the barrier block
   __shared__ int s_is_last;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -235,7 +273,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
           mbar_wait_backoff(&mdone[slot], par);
           mbar_wait_backoff(&xsum[slot], par);
         }
-        const int tiles = min(TPS, nt - st * TPS);
+        const int wtiles = min(TPS, nt - st * TPS);
+        const int tiles = A8 ? (wtiles + 1) / 2 : wtiles;     // activation tiles (fp8: one per two 64-k weight tiles)
         // the loads complete on the stage's 'ready' barrier (what the MMA thread waits for, together with the dequant
         // arrivals); the row-sum warps wait on the same barrier phase
         if (TC_ABL(8)) { mbar_arrive(&afull[slot]); continue; }
@@ -243,7 +282,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
         for (int ti = 0; ti < tiles; ++ti)
           asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                        ::"r"(smem_u32(xring + slot * XSTAGE + ti * kTcXTile)), "l"(reinterpret_cast<uint64_t>(&amap)),
-                         "r"((kt0 + st * TPS + ti) * kBK), "r"(0), "r"(smem_u32(&afull[slot]))
+                         "r"((kt0 + st * TPS + (A8 ? 2 * ti : ti)) * kBK), "r"(0), "r"(smem_u32(&afull[slot]))
                        : "memory");
       }
     }
@@ -255,7 +294,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
     const int nst_u = __shfl_sync(0xffffffffu, nst, 0), nt_u = __shfl_sync(0xffffffffu, nt, 0);
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N = NM, M = 128 (cute::UMMA::InstrDescriptor)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcNM >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      // (fp8: a_format = b_format = 0 = E4M3)
+      const uint32_t idesc = A8 ? ((1u << 4) | ((uint32_t)(kTcNM >> 3) << 17) | ((uint32_t)(128 >> 4) << 24))
+                                : ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcNM >> 3) << 17) | ((uint32_t)(128 >> 4) << 24));
       // B smem descriptor (cute::UMMA::SmemDescriptor): K-major, SWIZZLE_128B, SBO = 1024 B (8-row groups), version 1
       const uint64_t desc_hi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
       const uint32_t xbase = smem_u32(xring);
@@ -266,9 +307,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
         tc_fence_after();
         TC_TRACE(1, g);
         const int tiles = min(TPS, nt_u - st * TPS);
+        if (A8) {  // an activation tile = 128 k = two weight tiles = four K=32 steps
+#pragma unroll
+          for (int xi = 0; xi < XTPS; ++xi) {
+            if (2 * xi < tiles) {
+              const uint32_t xaddr = xbase + xs * XSTAGE + xi * kTcXTile;
+              const uint64_t bdesc0 = desc_hi | (uint64_t)(((xaddr >> 4) & 0x3FFF) | (1u << 16));
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                const int ti = 2 * xi + (kk >> 1);
+                if (ti < tiles && !TC_ABL(4))
+                  tc_mma_ts_f8(tmem + kTcColsD, tmem + kTcColsA + ab * ABUF + ti * ACOLS + (kk & 1) * 8, bdesc0 + (uint64_t)(2 * kk), idesc,
+                               (st > 0 || xi > 0 || kk > 0) ? 1u : 0u);
+              }
+            }
+          }
+        }
 #pragma unroll
         for (int ti = 0; ti < TPS; ++ti) {
-          if (ti < tiles) {
+          if (!A8 && ti < tiles) {
             const uint32_t xaddr = xbase + xs * XSTAGE + ti * kTcXTile;
             // start-address field is (addr >> 4): a k16 step (32 B) inside the swizzle atom is +2
             const uint64_t bdesc0 = desc_hi | (uint64_t)(((xaddr >> 4) & 0x3FFF) | (1u << 16));
@@ -296,11 +353,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
     // ===================== row sums of the landed activation tiles (row = xt) =====================
     const int xt = tid - 192;  // 0..63
     float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+    if (A8) {  // the quantizer already summed every 64-k tile of every row: add this unit's tiles; stage the token scales
+      pdl_wait();
+      if (xt < p.M) {
+        const float* ts = p.tile_sums + (size_t)xt * p.KT;
+        for (int kt = kt0; kt < kt1; ++kt) r0 += ts[kt];
+        ascale[xt] = p.a_scale[xt];
+      } else {
+        ascale[xt] = 0.f;
+      }
+    }
     for (int st = 0; st < nst; ++st) {
       const int g = gbase + st;
       const int slot = g % kTcNSX;
       mbar_wait(&afull[slot], (g / kTcNSX) & 1);  // stage ready (implies its activation tiles landed)
-      const int tiles = (TC_ABL(1) || WBITS == 16) ? 0 : min(TPS, nt - st * TPS);  // bf16 weights: no zero-point term
+      const int tiles = (TC_ABL(1) || WBITS == 16 || A8) ? 0 : min(TPS, nt - st * TPS);  // bf16 weights: no zero-point term
       for (int ti = 0; ti < tiles; ++ti) {
         const uint32_t rbase = smem_u32(xring + slot * XSTAGE + ti * kTcXTile) + xt * 128;
 #pragma unroll
@@ -350,7 +417,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
         if (ti < tiles) {
           const uint32_t wt = wring_u + slot * WSTAGE + ti * TILE_BYTES;
           const uint32_t acol = trow + kTcColsA + ab * ABUF + ti * ACOLS;
-          if (WBITS == 4) {
+          if (A8) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {  // chunk c = 32 k = one K=32 step
+              const uint4 wv = lds128(wt + woff[c]);
+              uint32_t a[8];
+              nib8_to_e4m3(wv.x, a[0], a[1]);
+              nib8_to_e4m3(wv.y, a[2], a[3]);
+              nib8_to_e4m3(wv.z, a[4], a[5]);
+              nib8_to_e4m3(wv.w, a[6], a[7]);
+              tc_st8(acol + c * 8, a);
+            }
+          } else if (WBITS == 4) {
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
               const uint4 wv = lds128(wt + woff[c]);
@@ -421,6 +499,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
       // weight ring is already receiving the next unit's first stages)
       float* fsw = reinterpret_cast<float*>(xring) + (grp * 32) * kBN + r;
       const float* sm = suma + grp * 32;
+      if (A8) {  // plain codes (no +16 bias in the fp8 operand) and the token's activation scale
+        const float zz = sz.y - 16.f;
+        const float* as = ascale + grp * 32;
+#pragma unroll
+        for (int m4 = 0; m4 < 32; m4 += 4) {
+          const float4 sa = *reinterpret_cast<const float4*>(sm + m4);
+          const float4 sc = *reinterpret_cast<const float4*>(as + m4);
+          fsw[(m4 + 0) * kBN] = sz.x * sc.x * (__uint_as_float(d[m4 + 0]) - zz * sa.x);
+          fsw[(m4 + 1) * kBN] = sz.x * sc.y * (__uint_as_float(d[m4 + 1]) - zz * sa.y);
+          fsw[(m4 + 2) * kBN] = sz.x * sc.z * (__uint_as_float(d[m4 + 2]) - zz * sa.z);
+          fsw[(m4 + 3) * kBN] = sz.x * sc.w * (__uint_as_float(d[m4 + 3]) - zz * sa.w);
+        }
+      } else {
 #pragma unroll
       for (int m4 = 0; m4 < 32; m4 += 4) {
         const float4 sa = *reinterpret_cast<const float4*>(sm + m4);
@@ -428,6 +519,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
         fsw[(m4 + 1) * kBN] = sz.x * (__uint_as_float(d[m4 + 1]) - sz.y * sa.y);
         fsw[(m4 + 2) * kBN] = sz.x * (__uint_as_float(d[m4 + 2]) - sz.y * sa.z);
         fsw[(m4 + 3) * kBN] = sz.x * (__uint_as_float(d[m4 + 3]) - sz.y * sa.w);
+      }
       }
     }
   }
@@ -602,13 +694,13 @@ int tc_smem_bytes(int wbits) {
   const int tps = wbits == 4 ? 4 : 2;
   const int wstage = tps * (wbits == 4 ? 4096 : (wbits == 8 ? 8192 : 16384));
   const int nsw = wbits == 16 ? 4 : kTcNSW;
-  return 1024 + kTcNSX * tps * kTcXTile + nsw * wstage + kTcNM * 4 + 48 * 8 + 64;
+  return 1024 + kTcNSX * tps * kTcXTile + nsw * wstage + kTcNM * 4 + 96 * 8 + 64;  // barrier block: 25 barriers, TMEM slot, 64 scales
 }
 
 cudaError_t tc_configure(int wbits) {
   cudaError_t e = cudaSuccess;
   auto cfg = [&](auto kern) { if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(wbits)); };
-  if (wbits == 4) { cfg(wq_gemm_tc_kernel<4, false>); cfg(wq_gemm_tc_kernel<4, true>); }
+  if (wbits == 4) { cfg(wq_gemm_tc_kernel<4, false>); cfg(wq_gemm_tc_kernel<4, true>); cfg(wq_gemm_tc_kernel<4, false, true>); cfg(wq_gemm_tc_kernel<4, true, true>); }
   else if (wbits == 16) { cfg(wq_gemm_tc_kernel<16, false>); cfg(wq_gemm_tc_kernel<16, true>); }
   else { cfg(wq_gemm_tc_kernel<8, false>); cfg(wq_gemm_tc_kernel<8, true>); }
   return e;
@@ -634,11 +726,12 @@ cudaError_t tc_launch(int wbits, const TcLaunch& a, cudaStream_t stream) {
   if (!enc) return cudaErrorNotSupported;
   // activations A[M, K] bf16, row stride lda: box = 64 k x 64 rows, 128B swizzle, zero fill outside [M, K]
   alignas(64) CUtensorMap amap;
+  const bool a8 = a.a_scale != nullptr;  // fp8 activations: bytes, 128 k per 128-byte swizzle row
   const cuuint64_t gdim[2] = {(cuuint64_t)a.K, (cuuint64_t)a.M};
-  const cuuint64_t gstride[1] = {(cuuint64_t)a.lda * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kTcNM};
+  const cuuint64_t gstride[1] = {(cuuint64_t)a.lda * (a8 ? 1 : 2)};
+  const cuuint32_t box[2] = {(cuuint32_t)(a8 ? 2 * kBK : kBK), (cuuint32_t)kTcNM};
   const cuuint32_t estr[2] = {1, 1};
-  if (enc(&amap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(a.A), gdim, gstride, box, estr,
+  if (enc(&amap, a8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(a.A), gdim, gstride, box, estr,
           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return cudaErrorInvalidValue;
@@ -647,6 +740,7 @@ cudaError_t tc_launch(int wbits, const TcLaunch& a, cudaStream_t stream) {
   p.packed = a.packed; p.sz = a.sz; p.A = a.A; p.lda = a.lda; p.C = a.C; p.ldc = a.ldc; p.bias = a.bias; p.residual = a.residual;
   p.ws = a.ws; p.counters = a.counters; p.M = a.M; p.N = a.N; p.K = a.K; p.Np = a.Np; p.KT = a.KT; p.NG = a.NG; p.S = a.S;
   p.act = a.act; p.alpha = a.alpha;
+  p.a_scale = a.a_scale; p.tile_sums = a.tile_sums;
   p.dbg = 0;
 #ifdef B2_TC_ABLATE
   if (const char* e = getenv("B2_TC_ABLATE")) p.dbg = atoi(e);
@@ -660,6 +754,11 @@ cudaError_t tc_launch(int wbits, const TcLaunch& a, cudaStream_t stream) {
   const int grid = (persist && units > sm_count()) ? sm_count() : units;
   const bool multi = units > grid;
   const size_t smem = (size_t)tc_smem_bytes(wbits);
+  if (a8) {
+    if (wbits != 4) return cudaErrorNotSupported;
+    return multi ? launch(wq_gemm_tc_kernel<4, true, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap)
+                 : launch(wq_gemm_tc_kernel<4, false, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap);
+  }
   if (wbits == 4)
     return multi ? launch(wq_gemm_tc_kernel<4, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap)
                  : launch(wq_gemm_tc_kernel<4, false>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap);

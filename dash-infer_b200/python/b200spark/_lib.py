@@ -12,8 +12,8 @@ SYMBOLS = [
     "b2_status_string", "b2_last_error", "b2_version", "b2_set_pdl",
     "b2_gemm_wq_create", "b2_gemm_wq_destroy", "b2_gemm_wq_packed_bytes", "b2_gemm_wq_prepare_weights",
     "b2_gemm_wq_prepare_swiglu", "b2_gemm_wq_attach_packed", "b2_gemm_wq_workspace_bytes", "b2_gemm_wq_run", "b2_gemm_wq_run_fused", "b2_gemm_wq_sumsq_parts",
-    "b2_gemm_wq_algo_bytes",
-    "b2_span_bytes", "b2_span_cache_append", "b2_span_attn_create", "b2_span_attn_destroy",
+    "b2_gemm_wq_algo_bytes", "b2_quant_fp8", "b2_gemm_wq_run_fp8",
+    "b2_span_bytes", "b2_span_cache_append", "b2_span_context_copy", "b2_span_attn_create", "b2_span_attn_destroy",
     "b2_span_attn_workspace_bytes", "b2_span_attn_run", "b2_span_attn_algo_bytes",
     "b2_rmsnorm", "b2_rotary", "b2_binary", "b2_embedding", "b2_argmax", "b2_argmax_shard", "b2_argmax_merge", "b2_lens_add",
     "b2_comm_create", "b2_comm_destroy", "b2_comm_buffer_bytes", "b2_comm_export", "b2_comm_connect", "b2_comm_connect_pointers",
@@ -76,8 +76,11 @@ def _load():
         "b2_gemm_wq_run_fused": (i32, [vp, vp, i64, vp, i64, i32, vp, vp, i32, f32, vp, sz, C.POINTER(GemmFuse), vp]),
         "b2_gemm_wq_sumsq_parts": (i32, [vp]),
         "b2_gemm_wq_algo_bytes": (sz, [vp, i32]),
+        "b2_quant_fp8": (i32, [vp, i64, vp, vp, vp, vp, i32, i32, f32, vp]),
+        "b2_gemm_wq_run_fp8": (i32, [vp, vp, i64, vp, vp, vp, i64, i32, vp, vp, i32, f32, vp, sz, vp]),
         "b2_span_bytes": (sz, [C.POINTER(SpanCfg)]),
         "b2_span_cache_append": (i32, [C.POINTER(SpanCfg), vp, vp, vp, vp, vp, i32, C.POINTER(RopeCfg), vp]),
+        "b2_span_context_copy": (i32, [C.POINTER(SpanCfg), vp, vp, i64, i32, vp]),
         "b2_span_attn_create": (i32, [C.POINTER(vp), C.POINTER(SpanCfg), i32]),
         "b2_span_attn_destroy": (i32, [vp]),
         "b2_span_attn_workspace_bytes": (sz, [vp, i32, i32]),

@@ -216,19 +216,19 @@ class DecodeStack:
 
     # ------------------------------------------------------------------ cache fill
     def set_context(self, ctx, seed=4321):
-        """Fill every layer's cache with `ctx` tokens of N(0,1) rows THROUGH the append kernel (so quantized spans carry
-        realistic params), and set the sequence lengths."""
-        cfg = self.cfg
+        """Fill every layer's cache with `ctx` tokens of N(0,1) rows through the prefill-side span writer
+        (b2_span_context_copy: quantized spans carry realistic params, bytes identical to `ctx` appends), and set the
+        sequence lengths."""
         gen = torch.Generator(device=self.device).manual_seed(seed)
-        width = (self.nH_l + 2 * self.nG_l) * 128
-        pos = torch.zeros(self.B, dtype=torch.int32, device=self.device)
-        for t in range(ctx):
-            rows = torch.randn(self.B, width, generator=gen, device=self.device).to(torch.bfloat16)
+        nG = self.nG_l
+        kw, vw = nG * 128, nG * 128
+        for b in range(self.Bmax):
+            rows = torch.randn(ctx, kw + vw, generator=gen, device=self.device).to(torch.bfloat16)
             for L in self.layers:
-                ops.cache_append(L["cache"], rows, pos, q_out=self.q)
-            pos += 1
-        self.lens_old.fill_(ctx)
-        self.lens_new.fill_(ctx + 1)
+                ops.context_copy(L["cache"], "k", b, rows[:, :kw])
+                ops.context_copy(L["cache"], "v", b, rows[:, kw:])
+        self._lens_old.fill_(ctx)
+        self._lens_new.fill_(ctx + 1)
         torch.cuda.synchronize()
 
     # ------------------------------------------------------------------ one decode step (eager or captured)

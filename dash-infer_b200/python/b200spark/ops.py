@@ -104,6 +104,19 @@ class GemmWQ:
                                        float(alpha), _ptr(wsb), wsb.numel(), C.byref(f), _stream()), "b2_gemm_wq_run_fused")
         return out
 
+    def run_fp8(self, q8, ws, out=None, act=ACT_NONE, alpha=1.0, residual=None):
+        """fp8-e4m3 activations (a Fp8Act from quant_fp8) x int4 per-channel weights on tcgen05 kind::f8f6f4."""
+        if self.pair:
+            act = _lib.ACT_SWIGLU
+        M = q8.y.shape[0]
+        if out is None:
+            out = torch.empty(M, self.N, dtype=torch.bfloat16, device=q8.y.device)
+        wsb = ws.reserve(max(self.workspace_bytes(max(M, 17)), 16))
+        check(lib.b2_gemm_wq_run_fp8(self.h, _ptr(q8.y), q8.y.stride(0), _ptr(q8.scale), _ptr(q8.tile_sums), _ptr(out), out.stride(0), M,
+                                     _ptr(self.bias), _ptr(residual), act, float(alpha), _ptr(wsb), wsb.numel(), _stream()),
+              "b2_gemm_wq_run_fp8")
+        return out
+
     def run_allreduce(self, a, ws, comm, out, residual=None, alpha=1.0):
         """Row-parallel projection fused with its all-reduce over `comm` (b2_gemm_wq_run_allreduce).  Returns False when the
         configuration is not covered (M > 16, ...): the caller then runs the GEMM and b2_allreduce separately."""
@@ -219,6 +232,16 @@ def cache_append(cache, qkv, old_lens, q_out=None, rope=None):
     return q_out
 
 
+def context_copy(cache, which, b, src, seq_len=None):
+    """Prefill: write sequence b's K (which='k') or V ('v') rows src [seq, ..., n_groups*128 leading values per token] into its
+    spans (b2_span_context_copy).  src may be a strided view (e.g. the K part of a fused qkv tensor)."""
+    assert src.dtype == torch.bfloat16 and src.stride(-1) == 1
+    seq_len = src.shape[0] if seq_len is None else seq_len
+    tab = cache.k_tab if which == "k" else cache.v_tab
+    check(lib.b2_span_context_copy(C.byref(cache.cfg), C.c_void_p(tab.data_ptr() + b * cache.max_spans * 8), _ptr(src), src.stride(0),
+                                   int(seq_len), _stream()), "b2_span_context_copy")
+
+
 class SpanAttn:
     def __init__(self, cfg, max_batch):
         self.cfg = cfg
@@ -255,6 +278,26 @@ def rmsnorm(x, gamma, eps=1e-6, out=None):
     out = torch.empty_like(x) if out is None else out
     cols = x.shape[-1]
     check(lib.b2_rmsnorm(_ptr(out), _ptr(x), _ptr(gamma), x.numel() // cols, cols, float(eps), _stream()), "b2_rmsnorm")
+    return out
+
+
+class Fp8Act:
+    """fp8-e4m3 activations in the b2 layout: y uint8 [rows, cols] (k permuted inside groups of 8), scale fp32 [rows],
+    tile_sums fp32 [rows, ceil(cols/64)]."""
+
+    def __init__(self, rows, cols, device="cuda"):
+        self.y = torch.empty(rows, (cols + 15) // 16 * 16, dtype=torch.uint8, device=device)
+        self.scale = torch.empty(rows, dtype=torch.float32, device=device)
+        self.tile_sums = torch.empty(rows, (cols + 63) // 64, dtype=torch.float32, device=device)
+        self.cols = cols
+
+
+def quant_fp8(x, gamma=None, eps=1e-6, out=None):
+    """Per-token fp8 quantization (optionally fused with RMSNorm) for GemmWQ.run_fp8."""
+    rows, cols = x.shape
+    out = Fp8Act(rows, cols, x.device) if out is None else out
+    check(lib.b2_quant_fp8(_ptr(out.y), out.y.stride(0), _ptr(out.scale), _ptr(out.tile_sums), _ptr(x), _ptr(gamma), rows, cols,
+                           float(eps), _stream()), "b2_quant_fp8")
     return out
 
 

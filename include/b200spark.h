@@ -18,6 +18,7 @@
  *   b2_span_bytes         CacheUtils::GetSpanSizeInBytes  csrc/runtime/cache/virtual_cache.cpp:202-232
  *   b2_span_cache_append  cuda::DecoderCacheAppendLauncher
  *                           csrc/core/kernel/cuda/cache/decoder_cache_append.cuh:102-185
+ *   b2_span_context_copy  cuda::ContextSpanCopyLauncher  csrc/core/kernel/cuda/cache/context_span_copy.cuh:220-245
  *   b2_span_attn_*        span::CreateHandle/GetDeviceWorkspaceSize/Run/DestroyHandle
  *                           span-attention/include/spanattn/span_attn.h:108-175
  *   b2_comm_*, b2_allreduce, b2_allgather, b2_gemm_wq_run_allreduce
@@ -128,6 +129,21 @@ int b2_gemm_wq_sumsq_parts(b2_gemm_wq_t handle);
 int b2_gemm_wq_run_fused(b2_gemm_wq_t handle, const void* A, int64_t lda, void* C, int64_t ldc, int M,
                          const void* bias, const void* residual, int activation, float alpha,
                          void* workspace, size_t workspace_bytes, const b2_gemm_fuse* fuse, void* stream);
+/* FP8 activations ("next" row f3; BASELINE config "GPTQ-int4, fp8 activations"): fp8-e4m3 activations x int4 weights on
+ * the tcgen05 tensor cores (kind::f8f6f4, K = 32 per MMA).  Beyond the reference (its FP8 operator is per-tensor A8W8 through
+ * cuBLASLt, csrc/core/operator/general/gemm_lowp/gemm_fp8_a8w8_gpu.cpp:325-395), so the accuracy contract is its own:
+ *   C[m,n] = act(alpha * scale_a[m] * s_n * (sum_k a8[m,k] q[k,n] - z_n sum_k a8[m,k]) + bias) (+ residual)
+ * exact products (e4m3 x e4m3) and fp32 accumulation: the only loss is the activation quantization itself.
+ * b2_quant_fp8 produces the operands: y = e4m3(x / scale[r]) with scale[r] = max|x[r,:]| / 448 (optionally after a fused
+ * RMSNorm: gamma != NULL), stored in the "b2 fp8 activation layout" (inside every aligned group of 8 k the bytes hold
+ * k = 0,2,4,6,1,3,5,7), plus tile_sums[r][ceil(cols/64)] = per-64-k sums of the quantized values.  ldy in bytes (>= cols,
+ * multiple of 16).  b2_gemm_wq_run_fp8: int4 per-channel weights only (B2_ERR_UNSUPPORTED otherwise); workspace as for
+ * b2_gemm_wq_run at M >= 17. */
+int b2_quant_fp8(void* y, int64_t ldy, float* scale, float* tile_sums, const void* x, const void* gamma, int rows, int cols,
+                 float eps, void* stream);
+int b2_gemm_wq_run_fp8(b2_gemm_wq_t handle, const void* A8, int64_t lda_bytes, const float* a_scale, const float* tile_sums,
+                       void* C, int64_t ldc, int M, const void* bias, const void* residual, int activation, float alpha,
+                       void* workspace, size_t workspace_bytes, void* stream);
 /* Algorithmic bytes one run at this M must read from HBM (weights + params + A + C). */
 size_t b2_gemm_wq_algo_bytes(b2_gemm_wq_t handle, int M);
 
@@ -165,6 +181,17 @@ typedef struct {
 int b2_span_cache_append(const b2_span_cfg* cfg, void* const* k_spans, void* const* v_spans,
                          void* q_out, const void* qkv, const int32_t* old_lens, int batch,
                          const b2_rope_cfg* rope, void* stream);
+
+/* Prefill side of the cache ("next" row f4): slice one sequence's contiguous K (or V) rows into its spans, quantizing like
+ * the append does (replaces cuda::ContextSpanCopyLauncher, csrc/core/kernel/cuda/cache/context_span_copy.cuh:47-106,220-245).
+ *   spans        device array of this sequence's span pointers (one row of a span table), K or V
+ *   src          [seq_len][token_stride] FT, the n_groups * head_size values of a token contiguous at its start
+ *                (token_stride = n_groups * head_size for a packed [seq, nG, head] tensor; a larger stride reads K or V
+ *                straight out of a fused qkv activation)
+ * Tokens 0 .. seq_len-1 are written; unlike the reference (which quantizes whole spans and so reads src up to the next span
+ * multiple) rows >= seq_len are left untouched. */
+int b2_span_context_copy(const b2_span_cfg* cfg, void* const* spans, const void* src, int64_t token_stride, int seq_len,
+                         void* stream);
 
 /* Attention handle (replaces span::CreateHandle/DestroyHandle, span_attn.h:108-133).  Unlike the
  * reference it is created ONCE per op (not per layer per step): tile scheduling happens on the
