@@ -856,7 +856,9 @@ static int rows_per_launch(const b2_gemm_wq* h) {
 
 static bool use_tc(const b2_gemm_wq* h, int M) {
   static const int min_m = env_int("B2_GEMM_TC_MIN_M", 17);
-  return h->group_tiles == 0 && M >= min_m;  // int4 / int8 per-channel and dense bf16 (lm_head)
+  static const int grouped = env_int("B2_GEMM_TC_GROUPED", 1);
+  // int4 / int8 per-channel, dense bf16 (lm_head), and int4 sub-channel (the scale is applied to the weights in the dequant warps)
+  return M >= min_m && (h->group_tiles == 0 || (grouped && h->d.wbits == 4));
 }
 
 static int make_tc_plan(b2_gemm_wq* h) {
@@ -996,6 +998,7 @@ static int run_impl(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, int64_t
       a.M = (M - m0) > kTcMaxM ? kTcMaxM : (M - m0);
       a.N = h->d.N; a.K = h->d.K; a.Np = h->Np; a.KT = h->KT; a.NG = h->NG; a.S = h->tc_S;
       a.act = activation; a.alpha = alpha;
+      a.group_tiles = h->group_tiles;
       cudaError_t e = tc_launch(h->d.wbits, a, stream);
       if (e != cudaSuccess) {
         set_last_error("wq_gemm_tc launch", e);

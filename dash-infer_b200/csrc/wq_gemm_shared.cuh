@@ -37,6 +37,7 @@ struct TcLaunch {
   float alpha;
   const float* a_scale = nullptr;    // != NULL: A is fp8-e4m3 in the b2 fp8 activation layout (lda in bytes)
   const float* tile_sums = nullptr;  // [M][KT] sums of the quantized activations per 64-k tile
+  int group_tiles = 0;               // > 0: sub-channel weights, k-tiles per quantization group (sz is [G][Np])
 };
 // GEMV without global split-K (wq_gemv2.cu)
 struct Gemv2Launch {

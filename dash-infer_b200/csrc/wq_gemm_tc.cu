@@ -145,6 +145,8 @@ struct TcParams {
   // fp8 activations (A8 instantiation): per-token scale [M] and per-(row, 64-k tile) sums of the quantized values [M][KT]
   const float* a_scale;
   const float* tile_sums;
+  int nm;           // MMA N (batch columns): 64, or 32 when M <= 32 (half the tensor-pipe time and activation traffic)
+  int group_tiles;  // GROUPED instantiation: k-tiles per quantization group; sz is [G][Np]
   int dbg;  // ablation bitmask, only honoured when compiled with -DB2_TC_ABLATE (tools/tc_ablate.py)
 };
 
@@ -159,7 +161,12 @@ struct TcParams {
 // MULTI: a CTA walks several units (more units than SMs); the single-unit instantiation folds the unit loop away
 // A8: fp8-e4m3 activations (b2_gemm_wq_run_fp8, int4 weights only): the int4 codes go to TMEM as exact e4m3 bytes, the MMAs
 // are kind::f8f6f4 with K = 32 (half the MMAs and half the TMEM stores of the bf16 path), an activation tile is 128 k wide.
-template <int WBITS, bool MULTI, bool A8 = false>
+// GROUPED: sub-channel weights (GPTQ g128 ...): the (scale, zero) of a channel changes every group_tiles k-tiles, so the affine
+// dequantisation cannot wait for the accumulator.  The dequant warps apply it to the weights instead — exact integer (q - 8)
+// in bf16, then ONE fused multiply-add per two weights: w = (q - 8) * s + (8 - z) * s, rounded to bf16 once — which is what
+// the reference's kernels (dequant in FT, gemm_lowp_utils.cuh:28-47) and its CPU path (weights stored in the model dtype)
+// feed their GEMMs with; the accumulator then needs no zero-point term and no row sums.
+template <int WBITS, bool MULTI, bool A8 = false, bool GROUPED = false>
 __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap amap) {
   constexpr int TILE_BYTES = WBITS == 4 ? 4096 : (WBITS == 8 ? 8192 : 16384);
   constexpr int NCH = WBITS == 4 ? 2 : (WBITS == 8 ? 4 : 8);  // 16B chunks per row per k-tile
@@ -168,6 +175,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
   // commit / barrier round trip of the issuing thread (that round trip costs ~400 clocks, an MMA 45)
   constexpr int TPS = WBITS == 4 ? 4 : 2;
   static_assert(!A8 || WBITS == 4, "fp8 activations: int4 weights only");
+  static_assert(!GROUPED || (!A8 && WBITS != 16), "sub-channel weights: bf16 activations, int4 / int8");
+  const int XTILE_LD = p.nm * 128;             // bytes the TMA writes per activation tile (the tile slot stays 64 rows)
   constexpr int ACOLS = A8 ? 16 : (WBITS == 8 ? 64 : 32);  // TMEM columns of dequantized A per k-tile (int8: lo and hi planes)
   constexpr int XTPS = A8 ? TPS / 2 : TPS;     // activation tiles per stage (fp8: 128 k per 128-byte row)
   constexpr int ABUF = ACOLS * TPS;            // per stage (128 columns)
@@ -278,7 +287,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
         // the loads complete on the stage's 'ready' barrier (what the MMA thread waits for, together with the dequant
         // arrivals); the row-sum warps wait on the same barrier phase
         if (TC_ABL(8)) { mbar_arrive(&afull[slot]); continue; }
-        mbar_arrive_expect_tx(&afull[slot], tiles * kTcXTile);
+        mbar_arrive_expect_tx(&afull[slot], tiles * XTILE_LD);
         for (int ti = 0; ti < tiles; ++ti)
           asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                        ::"r"(smem_u32(xring + slot * XSTAGE + ti * kTcXTile)), "l"(reinterpret_cast<uint64_t>(&amap)),
@@ -292,11 +301,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
     // compiler, and a non-uniform operand costs an R2UR waterfall per MMA (see `tmem`)
     const int gb = __shfl_sync(0xffffffffu, gbase, 0);
     const int nst_u = __shfl_sync(0xffffffffu, nst, 0), nt_u = __shfl_sync(0xffffffffu, nt, 0);
+    const uint32_t nm_u = (uint32_t)__shfl_sync(0xffffffffu, p.nm, 0);
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N = NM, M = 128 (cute::UMMA::InstrDescriptor)
       // (fp8: a_format = b_format = 0 = E4M3)
-      const uint32_t idesc = A8 ? ((1u << 4) | ((uint32_t)(kTcNM >> 3) << 17) | ((uint32_t)(128 >> 4) << 24))
-                                : ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcNM >> 3) << 17) | ((uint32_t)(128 >> 4) << 24));
+      const uint32_t idesc = A8 ? ((1u << 4) | ((nm_u >> 3) << 17) | ((uint32_t)(128 >> 4) << 24))
+                                : ((1u << 4) | (1u << 7) | (1u << 10) | ((nm_u >> 3) << 17) | ((uint32_t)(128 >> 4) << 24));
       // B smem descriptor (cute::UMMA::SmemDescriptor): K-major, SWIZZLE_128B, SBO = 1024 B (8-row groups), version 1
       const uint64_t desc_hi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
       const uint32_t xbase = smem_u32(xring);
@@ -367,7 +377,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
       const int g = gbase + st;
       const int slot = g % kTcNSX;
       mbar_wait(&afull[slot], (g / kTcNSX) & 1);  // stage ready (implies its activation tiles landed)
-      const int tiles = (TC_ABL(1) || WBITS == 16 || A8) ? 0 : min(TPS, nt - st * TPS);  // bf16 weights: no zero-point term
+      const int tiles = (TC_ABL(1) || WBITS == 16 || A8 || GROUPED || xt >= p.nm) ? 0 : min(TPS, nt - st * TPS);  // (no zero-point term)
       for (int ti = 0; ti < tiles; ++ti) {
         const uint32_t rbase = smem_u32(xring + slot * XSTAGE + ti * kTcXTile) + xt * 128;
 #pragma unroll
@@ -392,7 +402,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
     const int q = warp & 3;             // TMEM lane quadrant this warp may access
     const int r = q * 32 + lane;        // output channel (row of the 128-row tile)
     // per-channel (scale, zero + bias constant): immutable, read before the wait
-    const float2 sz = WBITS == 16 ? make_float2(1.f, 0.f) : p.sz[ng * kBN + r];
+    const float2 sz = (WBITS == 16 || GROUPED) ? make_float2(1.f, 0.f) : p.sz[ng * kBN + r];
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     const uint32_t wring_u = smem_u32(wring);
     const bool tracer = tid == 64;
@@ -403,6 +413,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
     for (int st = (grp ^ gbase) & 1; st < nst; st += 2) {  // group = parity of the global stage index
       const int g = gbase + st;
       const int slot = g % NSW, ab = g % NAB;
+      // sub-channel weights: this stage's per-(group, channel) params are requested before the wait on the weights
+      uint32_t gs2[TPS], gc2[TPS];
+      if (GROUPED) {
+#pragma unroll
+        for (int ti = 0; ti < TPS; ++ti) {
+          const int kt = min(kt0 + st * TPS + ti, kt1 - 1);
+          const float2 z = __ldg(p.sz + (size_t)(kt / p.group_tiles) * p.Np + ng * kBN + r);  // (scale, zero + 16)
+          gs2[ti] = pack_bf16x2(z.x, z.x);
+          const float c = (24.f - z.y) * z.x;                                                  // (8 - zero) * scale
+          gc2[ti] = pack_bf16x2(c, c);
+        }
+      }
       mbar_wait(&wfull[slot], (g / NSW) & 1);
       if (tracer) TC_TRACE(4, g);
       if (g >= NAB) {  // A buffer ab was last read by stage g - NAB, whose commit went to mdone[(g - NAB) % NSX]
@@ -443,6 +465,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
                   a[4 * jw + 1] = lop3_and_or(__funnelshift_r(w, w, 4), kMask4, kMagic);
                   a[4 * jw + 2] = lop3_and_or(__funnelshift_r(w, w, 8), kMask4, kMagic);
                   a[4 * jw + 3] = lop3_and_or(__funnelshift_r(w, w, 12), kMask4, kMagic);
+                }
+                if (GROUPED) {  // (16 + q) - 24 = q - 8 exactly, then one fused multiply-add: (q - 8) s + (8 - z) s
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    uint32_t t2;
+                    asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(t2) : "r"(a[e]), "r"(0xC1C0C1C0u));
+                    asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(a[e]) : "r"(t2), "r"(gs2[ti]), "r"(gc2[ti]));
+                  }
                 }
                 if (!TC_ABL(16)) tc_st8(acol + (2 * c + h) * 8, a);
                 else if (a[0] + a[3] + a[5] + a[7] == 0x12345u) tc_st8(acol, a);  // keep the ALU work alive
@@ -700,7 +730,10 @@ int tc_smem_bytes(int wbits) {
 cudaError_t tc_configure(int wbits) {
   cudaError_t e = cudaSuccess;
   auto cfg = [&](auto kern) { if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(wbits)); };
-  if (wbits == 4) { cfg(wq_gemm_tc_kernel<4, false>); cfg(wq_gemm_tc_kernel<4, true>); cfg(wq_gemm_tc_kernel<4, false, true>); cfg(wq_gemm_tc_kernel<4, true, true>); }
+  if (wbits == 4) {
+    cfg(wq_gemm_tc_kernel<4, false>); cfg(wq_gemm_tc_kernel<4, true>); cfg(wq_gemm_tc_kernel<4, false, true>); cfg(wq_gemm_tc_kernel<4, true, true>);
+    cfg(wq_gemm_tc_kernel<4, false, false, true>); cfg(wq_gemm_tc_kernel<4, true, false, true>);
+  }
   else if (wbits == 16) { cfg(wq_gemm_tc_kernel<16, false>); cfg(wq_gemm_tc_kernel<16, true>); }
   else { cfg(wq_gemm_tc_kernel<8, false>); cfg(wq_gemm_tc_kernel<8, true>); }
   return e;
@@ -729,7 +762,10 @@ cudaError_t tc_launch(int wbits, const TcLaunch& a, cudaStream_t stream) {
   const bool a8 = a.a_scale != nullptr;  // fp8 activations: bytes, 128 k per 128-byte swizzle row
   const cuuint64_t gdim[2] = {(cuuint64_t)a.K, (cuuint64_t)a.M};
   const cuuint64_t gstride[1] = {(cuuint64_t)a.lda * (a8 ? 1 : 2)};
-  const cuuint32_t box[2] = {(cuuint32_t)(a8 ? 2 * kBK : kBK), (cuuint32_t)kTcNM};
+  // batches <= 32 run the MMAs with N = 32 and load 32-row activation tiles (B2_GEMM_TC_N32=0: always 64)
+  static const int n32 = [] { const char* e = getenv("B2_GEMM_TC_N32"); return e ? atoi(e) : 1; }();
+  const int nm = (n32 && a.M <= 32) ? 32 : kTcNM;
+  const cuuint32_t box[2] = {(cuuint32_t)(a8 ? 2 * kBK : kBK), (cuuint32_t)nm};
   const cuuint32_t estr[2] = {1, 1};
   if (enc(&amap, a8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(a.A), gdim, gstride, box, estr,
           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -741,6 +777,7 @@ cudaError_t tc_launch(int wbits, const TcLaunch& a, cudaStream_t stream) {
   p.ws = a.ws; p.counters = a.counters; p.M = a.M; p.N = a.N; p.K = a.K; p.Np = a.Np; p.KT = a.KT; p.NG = a.NG; p.S = a.S;
   p.act = a.act; p.alpha = a.alpha;
   p.a_scale = a.a_scale; p.tile_sums = a.tile_sums;
+  p.nm = nm; p.group_tiles = a.group_tiles;
   p.dbg = 0;
 #ifdef B2_TC_ABLATE
   if (const char* e = getenv("B2_TC_ABLATE")) p.dbg = atoi(e);
@@ -758,6 +795,11 @@ cudaError_t tc_launch(int wbits, const TcLaunch& a, cudaStream_t stream) {
     if (wbits != 4) return cudaErrorNotSupported;
     return multi ? launch(wq_gemm_tc_kernel<4, true, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap)
                  : launch(wq_gemm_tc_kernel<4, false, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap);
+  }
+  if (a.group_tiles > 0) {
+    if (wbits != 4) return cudaErrorNotSupported;
+    return multi ? launch(wq_gemm_tc_kernel<4, true, false, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap)
+                 : launch(wq_gemm_tc_kernel<4, false, false, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap);
   }
   if (wbits == 4)
     return multi ? launch(wq_gemm_tc_kernel<4, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap)

@@ -132,7 +132,7 @@ class DecodeStack:
         self.collective = collective or os.environ.get("B2_TP_COLLECTIVE", "fused")
         self.comm = comm
         self.fuse_swiglu = fuse_swiglu
-        self.group_size = group
+        self.group_size, self.wbits = group, wbits
         self.device = device
         self.n_layers = layers if layers is not None else cfg.layers
         self.kv_mode = KV_MODES[kv]
@@ -319,7 +319,7 @@ class DecodeStack:
         # rows per launch above batch 16: 64 on the tcgen05 path (per-channel int4/int8, bf16 lm_head), 16 for sub-channel
         # weights (mma.sync path); below, one launch takes the whole batch
         hchunks = (self.B + 63) // 64 if self.B > 16 else 1
-        qchunks = ((self.B + 15) // 16 if self.group_size != -1 else hchunks) if self.B > 16 else 1
+        qchunks = ((self.B + 15) // 16 if (self.group_size != -1 and self.wbits != 4) else hchunks) if self.B > 16 else 1
         n += (qchunks - 1) * (4 if self.fuse_swiglu else 5) * len(self.layers) + (hchunks - 1)
         self.launches_per_step = n
 
