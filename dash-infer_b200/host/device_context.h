@@ -5,6 +5,7 @@
 
 #include <memory>
 
+#include "../../include/b200spark.h"
 #include "common.h"
 
 namespace allspark {
@@ -56,8 +57,9 @@ class DeviceContext {
   SpanCacheConfig::Ptr cache_config_;
 };
 
-// One stream per rank, like the reference.  NCCL/cuBLAS handles are not needed by the b200spark operators
-// (the TP exchange goes through torch.distributed / the caller's communicator — DESIGN.md "Multi-GPU").
+// One stream per rank, like the reference.  Where the reference's CUDAContext carries an ncclComm_t (GetNCCLComm), this one
+// carries the rank's b2_comm_t: the NVLink peer-memory communicator of include/b200spark.h (the engine creates it once per
+// rank next to where it calls ncclCommInitRank today and exchanges the 64-byte IPC handles over its existing bootstrap).
 class CUDAContext : public DeviceContext {
  public:
   CUDAContext() { cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking); }
@@ -70,10 +72,13 @@ class CUDAContext : public DeviceContext {
   int GetDeviceId() const { return device_id_; }
   cudaStream_t GetStream() const { return stream_; }
   void Synchronize() const override { cudaStreamSynchronize(stream_); }
+  void SetB2Comm(b2_comm_t c) { comm_ = c; }     // not owned
+  b2_comm_t GetB2Comm() const { return comm_; }
 
  private:
   cudaStream_t stream_ = nullptr;
   int rank_ = 0, nranks_ = 1, device_id_ = 0;
+  b2_comm_t comm_ = nullptr;
 };
 
 }  // namespace allspark

@@ -5,6 +5,7 @@
 #include <memory>
 #include <vector>
 
+#include "allreduce_op.h"
 #include "gemm_lowp_gpu.h"
 #include "span_attn_op_cuda.h"
 
@@ -96,6 +97,64 @@ int as_test_gemm_binary(const char* op_type, int M, int N, int K, int group_size
                         const void* residual_host, int binary_type, void* C_host) {
   return run_gemm(op_type, M, N, K, group_size, activation, alpha, A_host, w_host, w_dtype, scales_host, zeros_host, bias_host,
                   residual_host, binary_type, C_host);
+}
+
+// nranks AllReduce ops (one context / stream / communicator per "rank", all on the current device, wired through
+// b2_comm_connect_pointers) reduce nranks host vectors of `count` bf16; every rank's result is copied to out_all[r].
+int as_test_allreduce(int nranks, int64_t count, const void* in_all, void* out_all) {
+  try {
+    std::vector<b2_comm_t> comms(nranks, nullptr);
+    std::vector<void*> bufs(nranks, nullptr);
+    for (int r = 0; r < nranks; ++r) {
+      if (b2_comm_create(&comms[r], r, nranks, (size_t)count * 2) != B2_OK) return -4;
+      bufs[r] = b2_comm_local_buffer(comms[r]);
+    }
+    for (int r = 0; r < nranks; ++r)
+      if (b2_comm_connect_pointers(comms[r], bufs.data()) != B2_OK) return -5;
+    std::vector<std::unique_ptr<CUDAContext>> ctxs;
+    std::vector<std::unique_ptr<TensorMap>> maps;
+    std::vector<std::unique_ptr<AsOperator>> ops;
+    TensorMap weights;
+    for (int r = 0; r < nranks; ++r) {
+      ctxs.push_back(std::make_unique<CUDAContext>());
+      ctxs[r]->SetDtype(DataType::BFLOAT16);
+      ctxs[r]->SetRank(r, nranks);
+      ctxs[r]->SetB2Comm(comms[r]);
+      maps.push_back(std::make_unique<TensorMap>());
+      auto t = std::make_shared<AsTensor>("x", DeviceType::CUDA, DataType::BFLOAT16, DataMode::DENSE, Shape{1, count});
+      t->CopyDataFrom((const char*)in_all + (size_t)r * count * 2, (size_t)count * 2, DeviceType::CPU);
+      (*maps[r])["x"] = t;
+      OperatorProto proto;
+      proto.op_type_ = "AllReduce"; proto.op_name_ = "decoder.layer.0.attention.output.dense.allreduce";
+      proto.inputs_.push_back({"x"}); proto.outputs_.push_back({"x"});  // in place, like the reference graphs
+      ops.push_back(OpFactory::getInstance().GetOperator({"AllReduce", DeviceType::CUDA})());
+      TensorMap wb;
+      AsStatus st = ops[r]->InitV2(proto, *ctxs[r], weights, wb, maps[r].get(), nullptr);
+      if (st != AsStatus::ALLSPARK_SUCCESS) return (int)st;
+      st = ops[r]->CallReshape(nullptr);
+      if (st != AsStatus::ALLSPARK_SUCCESS) return (int)st;
+    }
+    cudaDeviceSynchronize();
+    for (int it = 0; it < 2; ++it) {  // twice: the second exchange runs on the other buffer parity (input = first result)
+      for (int r = 0; r < nranks; ++r) {
+        AsStatus st = ops[r]->CallForward(nullptr);
+        if (st != AsStatus::ALLSPARK_SUCCESS) return (int)st;
+      }
+      for (int r = 0; r < nranks; ++r) ctxs[r]->Synchronize();
+      if (it == 0)
+        for (int r = 0; r < nranks; ++r)
+          (*maps[r])["x"]->CopyDataTo((char*)out_all + (size_t)r * count * 2, (size_t)count * 2, DeviceType::CPU);
+    }
+    int rc = 0;
+    for (int r = 0; r < nranks; ++r) {
+      if (b2_comm_error(comms[r]) != B2_OK) rc = -6;
+      b2_comm_destroy(comms[r]);
+    }
+    return rc ? rc : (cudaGetLastError() == cudaSuccess ? 0 : -3);
+  } catch (const std::exception& e) {
+    AS_LOG_ERROR("as_test_allreduce: %s", e.what());
+    return -1;
+  }
 }
 
 // Decode `steps` tokens for `batch` sequences through DecOptMQA: per step op.Alloc + op.Forward with qkv_all[t]

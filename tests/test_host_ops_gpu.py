@@ -23,6 +23,8 @@ def _lib():
     lib.as_test_gemm_binary.restype = C.c_int
     lib.as_test_gemm_binary.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
                                         C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.as_test_allreduce.restype = C.c_int
+    lib.as_test_allreduce.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
     lib.as_test_span_attn.restype = C.c_int
     lib.as_test_span_attn.argtypes = [C.c_int] * 9 + [C.c_void_p, C.c_void_p]
     lib.as_test_registered.restype = C.c_int
@@ -33,7 +35,7 @@ def _lib():
 def test_host_library_loads_and_registers_ops():
     """CPU-safe: the operator library loads and the factory knows the reference's op-type strings."""
     lib = _lib()
-    for name in (b"GemmA16W4", b"GemmA16W8", b"Gemm", b"DecOptMHA", b"DecOptMQA"):
+    for name in (b"GemmA16W4", b"GemmA16W8", b"Gemm", b"DecOptMHA", b"DecOptMQA", b"AllReduce"):
         assert lib.as_test_registered(name) == 1, name
     assert lib.as_test_registered(b"GemmA8W8") == 0  # out of scope: must not pretend
 
@@ -196,3 +198,24 @@ def test_span_attention_operator_quantized_cache_modes(mode, layer):
             # allowance on top of the attention tolerance (identical-bytes attention parity: tests/test_attn_gpu.py)
             step = {KV.QUANT_I8: 1 / 255, KV.QUANT_U4: 1 / 15}[mode] * 8.0
             assert np.all(np.abs(got[t] - ref) <= 2e-3 + 2.0 ** -7 * np.abs(ref) + 0.1 * step), (t, np.abs(got[t] - ref).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_allreduce_operator(nranks):
+    """The AllReduce op type (allreduce_op.cpp:73-115) over b2_allreduce: nranks op instances, each with its own context,
+    stream and communicator on one device; in-place like the reference graphs; bit-exact fp32-rank-order sums."""
+    lib = _lib()
+    count = 16 * 8192
+    g = torch.Generator().manual_seed(nranks)
+    xs = torch.randn(nranks, count, generator=g).to(torch.bfloat16)
+    out = np.zeros((nranks, count), np.int16)
+    rc = lib.as_test_allreduce(nranks, count, _bf16_np(xs).ctypes.data, out.ctypes.data)
+    assert rc == 0, rc
+    acc = torch.zeros(count)
+    for r in range(nranks):
+        acc = acc + xs[r].float()
+    exp = acc.to(torch.bfloat16)
+    got = torch.from_numpy(out).view(torch.bfloat16)
+    for r in range(nranks):
+        assert torch.equal(got[r], exp), r

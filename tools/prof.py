@@ -30,9 +30,22 @@ torch.cuda.synchronize()
 if a.what == "step":
     st.step()  # plans / workspace growth outside the profiled region
     torch.cuda.synchronize()
+if a.what == "fp8":
+    from b200spark import ops
+    q8x = ops.quant_fp8(st.xn)
+    q8g = ops.quant_fp8(st.gate)
+    for L in st.layers:  # plans outside the profiled region
+        L["gateup"].op.run_fp8(q8x, st.ws, out=st.gate)
+    torch.cuda.synchronize()
 torch.cuda.profiler.start()
 for _ in range(a.iters):
-    if a.what == "gemm":
+    if a.what == "fp8":
+        for L in st.layers:
+            ops.quant_fp8(st.xn, out=q8x)
+            L["gateup"].op.run_fp8(q8x, st.ws, out=st.gate)
+            L["down"].op.run_fp8(q8g, st.ws, out=st.x)
+            L["qkv"].op.run_fp8(q8x, st.ws, out=st.qkv)
+    elif a.what == "gemm":
         for L in st.layers:
             if st.fuse_swiglu:
                 L["gateup"](st.xn, st.ws, out=st.gate)
