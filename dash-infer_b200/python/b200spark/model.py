@@ -36,6 +36,7 @@ class ModelConfig:
 QWEN2_7B = ModelConfig("Qwen2-7B", 3584, 28, 4, 18944, 28, 152064)
 LLAMA3_8B = ModelConfig("Llama-3-8B", 4096, 32, 8, 14336, 32, 128256, rope_base=5e5, eps=1e-5, qkv_bias=False)
 QWEN2_72B = ModelConfig("Qwen2-72B", 8192, 64, 8, 29568, 80, 152064)
+QWEN2_05B = ModelConfig("Qwen2-0.5B", 896, 14, 2, 4864, 24, 151936, head=64)   # config C0: the CPU-parity anchor
 TINY = ModelConfig("tiny-2L", 512, 8, 2, 1024, 2, 1024)
 
 KV_MODES = {"none": KV_NONE, "bf16": KV_NONE, "i8": KV_I8, "u4": KV_U4}
@@ -138,6 +139,7 @@ class DecodeStack:
         self.kv_mode = KV_MODES[kv]
         gen = torch.Generator(device=device).manual_seed(seed)
         H, nH, nG, I = cfg.hidden, cfg.n_heads, cfg.n_kv, cfg.inter
+        hd = self.head = cfg.head
         tp, r = tp_size, tp_rank
         self.nH_l, self.nG_l, self.I_l = nH // tp, nG // tp, I // tp
         nHl, nGl = self.nH_l, self.nG_l
@@ -149,9 +151,9 @@ class DecodeStack:
         for _ in range(self.n_layers):
             L = {}
             L["g1"] = (1.0 + 0.1 * torch.randn(H, generator=gen, device=device)).to(torch.bfloat16)
-            L["qkv"] = QuantLinear(H, (nH + 2 * nG) * 128, wbits, group, gen, device, batch, bias=cfg.qkv_bias, keep_ref=keep_ref,
+            L["qkv"] = QuantLinear(H, (nH + 2 * nG) * hd, wbits, group, gen, device, batch, bias=cfg.qkv_bias, keep_ref=keep_ref,
                                    shard=col_qkv)
-            L["o"] = QuantLinear(nH * 128, H, wbits, group, gen, device, batch, keep_ref=keep_ref, shard=row)
+            L["o"] = QuantLinear(nH * hd, H, wbits, group, gen, device, batch, keep_ref=keep_ref, shard=row)
             L["g2"] = (1.0 + 0.1 * torch.randn(H, generator=gen, device=device)).to(torch.bfloat16)
             if fuse_swiglu:
                 L["gateup"] = SwiGLULinear(H, I, wbits, group, gen, device, batch, keep_ref=keep_ref, shard=col_i)
@@ -161,7 +163,7 @@ class DecodeStack:
                 L["gate"] = QuantLinear(H, I, wbits, group, gen, device, batch, keep_ref=keep_ref, shard=col_i)
                 L["up"] = QuantLinear(H, I, wbits, group, gen, device, batch, keep_ref=keep_ref, shard=col_i)
             L["down"] = QuantLinear(I, H, wbits, group, gen, device, batch, keep_ref=keep_ref, shard=row)
-            L["cache"] = ops.SpanCache(batch, max_len, nHl, nGl, span, self.kv_mode, device)
+            L["cache"] = ops.SpanCache(batch, max_len, nHl, nGl, span, self.kv_mode, device, head=hd)
             self.layers.append(L)
         self.gf = (1.0 + 0.1 * torch.randn(H, generator=gen, device=device)).to(torch.bfloat16)
         self.vocab_l = cfg.vocab // tp
@@ -169,7 +171,7 @@ class DecodeStack:
                                    shard=("cols", TP.col_range_even(cfg.vocab, r, tp)) if tp > 1 else None)
         self.attn = ops.SpanAttn(self.layers[0]["cache"].cfg, batch)
         self.ws = ops.Workspace(device)
-        self.rope = (cfg.rope_base, 128)
+        self.rope = (cfg.rope_base, hd)
         # device-resident step state, allocated for the construction batch; set_batch() re-views it for a smaller batch
         self.Bmax = batch
         self._lens_old = torch.zeros(batch, dtype=torch.int32, device=device)
@@ -178,8 +180,8 @@ class DecodeStack:
         self._next_ids = torch.zeros(batch, dtype=torch.int64, device=device)
         bf = dict(dtype=torch.bfloat16, device=device)
         self._bufs = dict(x=torch.empty(batch, H, **bf), xn=torch.empty(batch, H, **bf),
-                          qkv=torch.empty(batch, (nHl + 2 * nGl) * 128, **bf), q=torch.empty(batch, nHl * 128, **bf),
-                          ao=torch.empty(batch, nHl * 128, **bf), gate=torch.empty(batch, self.I_l, **bf),
+                          qkv=torch.empty(batch, (nHl + 2 * nGl) * hd, **bf), q=torch.empty(batch, nHl * hd, **bf),
+                          ao=torch.empty(batch, nHl * hd, **bf), gate=torch.empty(batch, self.I_l, **bf),
                           up=torch.empty(batch, self.I_l, **bf), logits=torch.empty(batch, self.vocab_l, **bf))
         if tp > 1:
             if self.collective != "nccl" and self.comm is None:
@@ -221,8 +223,16 @@ class DecodeStack:
         sequence lengths."""
         gen = torch.Generator(device=self.device).manual_seed(seed)
         nG = self.nG_l
-        kw, vw = nG * 128, nG * 128
-        for b in range(self.Bmax):
+        kw, vw = nG * self.head, nG * self.head
+        if self.head != 128:  # the prefill writer covers head 128; small heads go through the append kernel
+            pos = torch.zeros(self.Bmax, dtype=torch.int32, device=self.device)
+            width = (self.nH_l + 2 * nG) * self.head
+            for t in range(ctx):
+                rows = torch.randn(self.Bmax, width, generator=gen, device=self.device).to(torch.bfloat16)
+                for L in self.layers:
+                    ops.cache_append(L["cache"], rows, pos, q_out=self._bufs["q"])
+                pos += 1
+        for b in range(self.Bmax if self.head == 128 else 0):
             rows = torch.randn(ctx, kw + vw, generator=gen, device=self.device).to(torch.bfloat16)
             for L in self.layers:
                 ops.context_copy(L["cache"], "k", b, rows[:, :kw])

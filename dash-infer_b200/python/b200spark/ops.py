@@ -193,12 +193,13 @@ class SpanCache:
     """Test/bench stand-in for the reference's CacheSpanManager + SpannedVirtualCache: owns span pages for one
     layer's K and V of a batch and the device pointer tables [batch, max_spans] the kernels walk."""
 
-    def __init__(self, batch, max_len, n_heads, n_groups, span_len=128, quant_mode=KV_NONE, device="cuda", pool=None, fill=0):
+    def __init__(self, batch, max_len, n_heads, n_groups, span_len=128, quant_mode=KV_NONE, device="cuda", pool=None, fill=0, head=128):
         """fill: byte the span pool is initialised with (the reference's span manager never zeroes frames; tests use
         0xFF = NaN patterns to prove no kernel consumes unwritten rows)."""
         self.batch, self.max_len = batch, max_len
         self.max_spans = (max_len + span_len - 1) // span_len
-        self.cfg = SpanCfg(DT_BF16, quant_mode, n_heads, n_groups, 128, span_len, self.max_spans, 0)
+        self.head = head
+        self.cfg = SpanCfg(DT_BF16, quant_mode, n_heads, n_groups, head, span_len, self.max_spans, 0)
         self.span_bytes = lib.b2_span_bytes(C.byref(self.cfg))
         assert self.span_bytes > 0, "bad span config"
         n = batch * self.max_spans
@@ -224,7 +225,7 @@ def cache_append(cache, qkv, old_lens, q_out=None, rope=None):
     cfg = cache.cfg
     B = qkv.shape[0]
     if q_out is None:
-        q_out = torch.empty(B, cfg.n_heads * 128, dtype=torch.bfloat16, device=qkv.device)
+        q_out = torch.empty(B, cfg.n_heads * cfg.head_size, dtype=torch.bfloat16, device=qkv.device)
     r = RopeCfg(float(rope[0]), int(rope[1]), 0) if rope is not None else None
     check(lib.b2_span_cache_append(C.byref(cfg), _ptr(cache.k_tab), _ptr(cache.v_tab), _ptr(q_out), _ptr(qkv),
                                    _ptr(old_lens), B, C.byref(r) if r is not None else None, _stream()),
@@ -256,7 +257,7 @@ class SpanAttn:
         if out is None:
             out = torch.empty_like(q)
         if scale is None:
-            scale = 1.0 / (128 ** 0.5)
+            scale = 1.0 / (self.cfg.head_size ** 0.5)
         wsb = ws.reserve(self.workspace_bytes(B, max_len))
         check(lib.b2_span_attn_run(self.h, _ptr(out), _ptr(q), _ptr(cache.k_tab), _ptr(cache.v_tab), _ptr(new_lens), B,
                                    int(max_len), _ptr(wsb), wsb.numel(), float(scale), _stream()), "b2_span_attn_run")

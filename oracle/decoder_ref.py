@@ -21,14 +21,19 @@ import torch
 from . import kvcache_ref as KV
 
 
+_EXACT = False  # set by RefDecoder(exact=True).step: no intermediate rounding at all (the "truth" both paths approximate)
+
+
 def _bf(x):
-    return x.to(torch.bfloat16)
+    return x.float() if _EXACT else x.to(torch.bfloat16)
 
 
 class RefDecoder:
-    def __init__(self, cfg, layers, embed, gf, lm_head, kv_mode=KV.QUANT_NONE):
-        """layers: list of dicts with g1,g2 (fp32 [H]) and qkv,o,gate,up,down = (W fp32 [K,N], bias or None)."""
-        self.cfg, self.kv_mode = cfg, kv_mode
+    def __init__(self, cfg, layers, embed, gf, lm_head, kv_mode=KV.QUANT_NONE, exact=False):
+        """layers: list of dicts with g1,g2 (fp32 [H]) and qkv,o,gate,up,down = (W fp32 [K,N], bias or None).
+        exact=True: the same graph on the same (bf16-valued) weights with fp32 activations and no rounding between operators —
+        not a reference path, but the yardstick for "how far is a bf16 implementation from the exact result" on deep stacks."""
+        self.cfg, self.kv_mode, self.exact = cfg, kv_mode, exact
         self.embed = _bf(embed)
         self.gf = gf.float()
         self.lm = _bf(lm_head)
@@ -51,7 +56,7 @@ class RefDecoder:
 
     def _gemm(self, x, wb, act=None):
         w, b = wb
-        y = torch.matmul(_bf(x), w).float()
+        y = torch.matmul(_bf(x), w.float() if self.exact else w).float()
         if b is not None:
             y = y + b
         if act == "silu":
@@ -59,9 +64,9 @@ class RefDecoder:
         return _bf(y)
 
     def _rope(self, x, pos):
-        # x: [n, 128] fp32 rows of one sequence; NeoX rotate-half, inv_freq = base^(-2i/d)
-        half = 64
-        inv = self.cfg.rope_base ** (-torch.arange(0, half, dtype=torch.float64) * 2.0 / 128.0)
+        # x: [n, head] fp32 rows of one sequence; NeoX rotate-half, inv_freq = base^(-2i/d)
+        half = x.shape[-1] // 2
+        inv = self.cfg.rope_base ** (-torch.arange(0, half, dtype=torch.float64) * 2.0 / float(2 * half))
         ang = (pos * inv)
         cs, sn = torch.cos(ang).float(), torch.sin(ang).float()
         a, b = x[:, :half], x[:, half:]
@@ -77,14 +82,23 @@ class RefDecoder:
 
     def step(self, ids, pos):
         """ids: int64 [B]; pos[b]: tokens already cached.  Returns (logits fp32 [B, vocab], next_ids)."""
+        global _EXACT
+        _EXACT = self.exact
+        try:
+            return self._step(ids, pos)
+        finally:
+            _EXACT = False
+
+    def _step(self, ids, pos):
         cfg = self.cfg
         nH, nG, hpg = cfg.n_heads, cfg.n_kv, cfg.n_heads // cfg.n_kv
+        hd = getattr(cfg, "head", 128)   # 128 everywhere except the parity anchor C0 (Qwen2-0.5B: 64)
         B = ids.shape[0]
         x = self.embed[ids]
         for li, L in enumerate(self.layers):
             xn = self._rms(x, L["g1"])
-            qkv = self._gemm(xn, L["qkv"]).float().reshape(B, nH + 2 * nG, 128)
-            ao = torch.zeros(B, nH, 128)
+            qkv = self._gemm(xn, L["qkv"]).float().reshape(B, nH + 2 * nG, hd)
+            ao = torch.zeros(B, nH, hd)
             for b in range(B):
                 qk = _bf(self._rope(qkv[b, :nH + nG], float(pos[b]))).float()
                 q, k, v = qk[:nH], qk[nH:], qkv[b, nH + nG:]
@@ -92,11 +106,11 @@ class RefDecoder:
                 self.v[li][b].append(self._store(v))
                 Kc = torch.stack(self.k[li][b], 1)  # [nG, T, 128]
                 Vc = torch.stack(self.v[li][b], 1)
-                qh = q.reshape(nG, hpg, 128)
-                s = torch.einsum("ghd,gtd->ght", qh.double(), Kc.double()) / math.sqrt(128.0)
+                qh = q.reshape(nG, hpg, hd)
+                s = torch.einsum("ghd,gtd->ght", qh.double(), Kc.double()) / math.sqrt(float(hd))
                 p = torch.softmax(s, dim=-1)
-                ao[b] = torch.einsum("ght,gtd->ghd", p, Vc.double()).float().reshape(nH, 128)
-            ao = _bf(ao.reshape(B, nH * 128))
+                ao[b] = torch.einsum("ght,gtd->ghd", p, Vc.double()).float().reshape(nH, hd)
+            ao = _bf(ao.reshape(B, nH * hd))
             x = _bf(self._gemm(ao, L["o"]).float() + x.float())
             xn = self._rms(x, L["g2"])
             g = self._gemm(xn, L["gate"], act="silu")
@@ -104,11 +118,11 @@ class RefDecoder:
             h = _bf(g.float() * u.float())
             x = _bf(self._gemm(h, L["down"]).float() + x.float())
         xn = self._rms(x, self.gf)
-        logits = torch.matmul(xn, self.lm).float()
+        logits = torch.matmul(xn, self.lm.float() if self.exact else self.lm).float()
         return logits, torch.argmax(logits, dim=-1)
 
 
-def from_stack(stack, kv_mode=KV.QUANT_NONE):
+def from_stack(stack, kv_mode=KV.QUANT_NONE, exact=False):
     """Build the oracle from a b200spark DecodeStack created with keep_ref=True (dense dequantized weights)."""
     layers = []
     for L in stack.layers:
@@ -116,7 +130,7 @@ def from_stack(stack, kv_mode=KV.QUANT_NONE):
         for k in ("qkv", "o", "gate", "up", "down"):
             d[k] = (L[k].ref, L[k].ref_bias)
         layers.append(d)
-    return RefDecoder(stack.cfg, layers, stack.embed.float().cpu(), stack.gf.float().cpu(), stack.lm_head.ref, kv_mode)
+    return RefDecoder(stack.cfg, layers, stack.embed.float().cpu(), stack.gf.float().cpu(), stack.lm_head.ref, kv_mode, exact=exact)
 
 
 # ---------------------------------------------------------------------------------------------------------------

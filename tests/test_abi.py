@@ -41,7 +41,11 @@ def test_param_validation_without_gpu():
     assert lib.b2_gemm_wq_create(C.byref(h), C.byref(bad)) == 6
     bad = _lib.GemmDesc(128, 128, 4, -1, _lib.DT_BF16, _lib.DT_I8, 8, 0)  # A16W4 is uint4x2 only (gemm_a16w4.cpp:104-110)
     assert lib.b2_gemm_wq_create(C.byref(h), C.byref(bad)) == 3
-    cfg = _lib.SpanCfg(_lib.DT_BF16, 0, 28, 4, 64, 128, 16, 0)  # head 64: unsupported like the reference
+    cfg = _lib.SpanCfg(_lib.DT_BF16, 0, 28, 4, 64, 128, 16, 0)  # head 64 (config C0): bf16 KV only
+    assert lib.b2_span_bytes(C.byref(cfg)) == 128 * 4 * 64 * 2
+    cfg = _lib.SpanCfg(_lib.DT_BF16, 1, 28, 4, 64, 128, 16, 0)  # head 64 with quantized KV: unsupported (like the reference)
+    assert lib.b2_span_bytes(C.byref(cfg)) == 0
+    cfg = _lib.SpanCfg(_lib.DT_BF16, 0, 28, 4, 96, 128, 16, 0)
     assert lib.b2_span_bytes(C.byref(cfg)) == 0
     cfg = _lib.SpanCfg(_lib.DT_BF16, 1, 28, 4, 128, 128, 16, 0)
     assert lib.b2_span_bytes(C.byref(cfg)) == 128 * 4 * 128 + 2 * 128 * 4 * 4  # virtual_cache.cpp:214-220
