@@ -58,6 +58,9 @@ struct GemmParams {
   const float* norm_sumsq;
   const __nv_bfloat16* norm_gamma;
   int norm_parts;
+  int cluster;    // 1: the S k-slices of a tile are one thread-block cluster; partial tiles are summed through distributed
+                  //    shared memory (no workspace, no counters)
+  int norm_self;  // 1: the kernel takes the row statistics itself while staging the activations (K == hidden)
   float norm_inv_hidden, norm_eps;
   float* sumsq_out;
   // optional fused all-reduce of the output over tensor-parallel ranks (b2_gemm_wq_run_allreduce)
@@ -161,12 +164,16 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
   const int ring_bytes = NST * T::STAGE_BYTES;
   const int XS = p.xt * 128 + 16;  // activation row stride (bytes), == 16 mod 128: conflict-free LDS.128
   uint8_t* xs = ring + ring_bytes;
-  float* fs = reinterpret_cast<float*>(xs + MP * XS);        // [MP][kBN] partial tile
+  uint8_t* grow = xs + MP * XS;                               // [xt*64] gamma slice of the chunk (self-contained norm)
+  float* fs = reinterpret_cast<float*>(grow + XS);           // [MP][kBN] partial tile
   float* suma = fs + MP * kBN;                                // [MP][groups per chunk] (or [MP])
   const int gpc = GROUPED ? p.xt / gt : 1;                    // groups per chunk
   float* sinv = suma + MP * gpc;                              // [MP] rsqrt(mean square) of the activation rows (norm fusion)
-  uint64_t* full = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sinv + MP + 4) + 7) & ~uintptr_t(7));
+  float* srs = sinv + MP;                                     // [MP] 1/rms of the rows (self-contained norm), else unused
+  uint64_t* full = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(srs + MP + 4) + 7) & ~uintptr_t(7));
   uint64_t* empty = full + NST;
+  uint64_t* xbar = empty + NST;  // activation rows of a chunk landed (bulk copies)
+  uint64_t* gbar = xbar + 1;     // gamma slice of a chunk landed
   __shared__ int s_is_last;
 
   const bool tr0 = blockIdx.x == 0 && tid == 0;
@@ -176,6 +183,8 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], kWarps);
     }
+    mbar_init(xbar, 1);
+    mbar_init(gbar, 1);
     fence_mbar_init();
   }
   __syncthreads();
@@ -214,6 +223,16 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[m][c] = facc[m][c] = 0.f;
 
+  // rows M..MP-1 of the MMA's batch dimension stay zero for the whole kernel
+  for (int i = p.M * XS + tid * 16; i < MP * XS; i += kWarps * 32 * 16) *reinterpret_cast<uint4*>(xs + i) = make_uint4(0, 0, 0, 0);
+  const int64_t k_first = (int64_t)kt0 * kBK;
+  if (p.norm_self && tid == 0) {  // gamma is immutable: its first slice travels ahead of the dependency wait
+    const int64_t left = ((int64_t)p.K - k_first) * 2;
+    const uint32_t gb = (uint32_t)max((int64_t)0, min((int64_t)min(p.xt, nt) * 128, left));
+    mbar_arrive_expect_tx(gbar, gb);
+    if (gb) bulk_g2s(grow, p.norm_gamma + k_first, gb, gbar);
+  }
+
   pdl_wait();  // activations / workspace / counters belong to the previous kernels from here on
   if (tr0) B2_TR(g_gemv_tr, 3);
 
@@ -241,44 +260,84 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
   for (int xc0 = 0; xc0 < nt; xc0 += p.xt) {  // p.xt is a multiple of TPS and of the quant group
     const int xn = min(p.xt, nt - xc0);
     if (xc0 > 0) named_bar_sync(1, kWarps * 32);  // previous chunk fully consumed
-    // ---- stage activations A[m][k-chunk] (bf16) -> xs (zero-fill m >= M, k >= K) and, in the same pass,
-    //      sum_k a[m][k] per (row, quant group): the zero-point term of the affine dequant
+    // ---- stage activations A[m][k-chunk] (bf16) -> xs: one bulk copy per live row (a single L2 round trip for the whole
+    //      chunk), then one pass over shared memory for sum_k a[m][k] per (row, quant group) — the zero-point term of the
+    //      affine dequant — the zero fill of k >= K and, with a fused RMSNorm, the scaling by gamma / the row statistics
     {
       const int64_t kbase = (int64_t)(kt0 + xc0) * kBK;
+      const int chunk = xc0 / p.xt;
+      const uint32_t rb = (uint32_t)max((int64_t)0, min((int64_t)xn * 128, ((int64_t)p.K - kbase) * 2));  // live bytes per row
+      if (tid == 0) {
+        fence_proxy_async();  // the previous chunk was read / rewritten through the generic proxy
+        if (p.norm_self && xc0 > 0) {
+          mbar_arrive_expect_tx(gbar, rb);
+          if (rb) bulk_g2s(grow, p.norm_gamma + kbase, rb, gbar);
+        }
+        mbar_arrive_expect_tx(xbar, rb * p.M);
+        if (rb)
+          for (int m = 0; m < p.M; ++m) bulk_g2s(xs + m * XS, p.A + (int64_t)m * p.lda + kbase, rb, xbar);
+      }
+      if (tr0 && xc0 == 0) B2_TR(g_gemv_tr, 12);
+      mbar_wait(xbar, chunk & 1);
+      if (p.norm_self) mbar_wait(gbar, chunk & 1);
+      if (tr0 && xc0 == 0) B2_TR(g_gemv_tr, 13);
       const int nvec = xn * 8;
       const int gvec = GROUPED ? gt * 8 : nvec;  // 16B vectors per quant group
+      const int lvec = rb >> 4;                  // live vectors per row
       for (int m = warp; m < MP; m += kWarps) {
-        const __nv_bfloat16* arow = p.A + (int64_t)m * p.lda + kbase;
         uint8_t* xrow = xs + m * XS;
         const bool mrow = m < p.M;
+        float ssq = 0.f;
         for (int v0 = 0, gi = 0; v0 < nvec; v0 += gvec, ++gi) {
           float sacc = 0.f;
-          for (int v = v0 + lane; v < v0 + gvec; v += 32) {
-            uint4 val = make_uint4(0, 0, 0, 0);
-            if (mrow && kbase + v * 8 < p.K) {
-              val = *reinterpret_cast<const uint4*>(arow + v * 8);
-              if (p.norm_sumsq) {  // same fp32 op order and rounding as rmsnorm_kernel: (x * inv) * gamma -> bf16
-                const uint4 gv = *reinterpret_cast<const uint4*>(p.norm_gamma + kbase + v * 8);
-                const float inv = sinv[m];
-                val.x = pack_bf16x2(bf16_lo(val.x) * inv * bf16_lo(gv.x), bf16_hi(val.x) * inv * bf16_hi(gv.x));
-                val.y = pack_bf16x2(bf16_lo(val.y) * inv * bf16_lo(gv.y), bf16_hi(val.y) * inv * bf16_hi(gv.y));
-                val.z = pack_bf16x2(bf16_lo(val.z) * inv * bf16_lo(gv.z), bf16_hi(val.z) * inv * bf16_hi(gv.z));
-                val.w = pack_bf16x2(bf16_lo(val.w) * inv * bf16_lo(gv.w), bf16_hi(val.w) * inv * bf16_hi(gv.w));
+          if (mrow) {
+            for (int v = v0 + lane; v < v0 + gvec; v += 32) {
+              uint4 val = make_uint4(0, 0, 0, 0);
+              if (v < lvec) {
+                val = *reinterpret_cast<const uint4*>(xrow + v * 16);
+                if (p.norm_self) {
+                  // self-contained RMSNorm: bf16(x * gamma) feeds the MMAs, sum x^2 of this CTA's k-slice is collected on
+                  // the way; the 1/rms factor is linear in the row and is applied to the reduced fp32 tile in the epilogue
+                  const uint4 gv = *reinterpret_cast<const uint4*>(grow + v * 16);
+                  const float x0 = bf16_lo(val.x), x1 = bf16_hi(val.x), x2 = bf16_lo(val.y), x3 = bf16_hi(val.y);
+                  const float x4 = bf16_lo(val.z), x5 = bf16_hi(val.z), x6 = bf16_lo(val.w), x7 = bf16_hi(val.w);
+                  ssq += (x0 * x0 + x1 * x1) + (x2 * x2 + x3 * x3) + (x4 * x4 + x5 * x5) + (x6 * x6 + x7 * x7);
+                  val.x = pack_bf16x2(x0 * bf16_lo(gv.x), x1 * bf16_hi(gv.x));
+                  val.y = pack_bf16x2(x2 * bf16_lo(gv.y), x3 * bf16_hi(gv.y));
+                  val.z = pack_bf16x2(x4 * bf16_lo(gv.z), x5 * bf16_hi(gv.z));
+                  val.w = pack_bf16x2(x6 * bf16_lo(gv.w), x7 * bf16_hi(gv.w));
+                  *reinterpret_cast<uint4*>(xrow + v * 16) = val;
+                } else if (p.norm_sumsq) {  // same fp32 op order and rounding as rmsnorm_kernel: (x * inv) * gamma -> bf16
+                  const uint4 gv = *reinterpret_cast<const uint4*>(p.norm_gamma + kbase + v * 8);
+                  const float inv = sinv[m];
+                  val.x = pack_bf16x2(bf16_lo(val.x) * inv * bf16_lo(gv.x), bf16_hi(val.x) * inv * bf16_hi(gv.x));
+                  val.y = pack_bf16x2(bf16_lo(val.y) * inv * bf16_lo(gv.y), bf16_hi(val.y) * inv * bf16_hi(gv.y));
+                  val.z = pack_bf16x2(bf16_lo(val.z) * inv * bf16_lo(gv.z), bf16_hi(val.z) * inv * bf16_hi(gv.z));
+                  val.w = pack_bf16x2(bf16_lo(val.w) * inv * bf16_lo(gv.w), bf16_hi(val.w) * inv * bf16_hi(gv.w));
+                  *reinterpret_cast<uint4*>(xrow + v * 16) = val;
+                }
+              } else {
+                *reinterpret_cast<uint4*>(xrow + v * 16) = val;  // k >= K
               }
+              sacc += (bf16_lo(val.x) + bf16_hi(val.x)) + (bf16_lo(val.y) + bf16_hi(val.y)) +
+                      (bf16_lo(val.z) + bf16_hi(val.z)) + (bf16_lo(val.w) + bf16_hi(val.w));
             }
-            *reinterpret_cast<uint4*>(xrow + v * 16) = val;
-            sacc += (bf16_lo(val.x) + bf16_hi(val.x)) + (bf16_lo(val.y) + bf16_hi(val.y)) +
-                    (bf16_lo(val.z) + bf16_hi(val.z)) + (bf16_lo(val.w) + bf16_hi(val.w));
-          }
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+            for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+          }
           if (lane == 0) {
             if (GROUPED) suma[m * gpc + gi] = sacc;
             else suma[m] = (xc0 == 0 ? 0.f : suma[m]) + sacc;
           }
         }
+        if (p.norm_self) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
+          if (lane == 0) sinv[m] = (xc0 == 0 ? 0.f : sinv[m]) + ssq;
+        }
       }
     }
+    if (tr0 && xc0 == 0) B2_TR(g_gemv_tr, 14);
     named_bar_sync(1, kWarps * 32);
     if (tr0 && xc0 == 0) B2_TR(g_gemv_tr, 4);
 
@@ -339,10 +398,105 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
 
   const int ctid = tid;
   const int MPK = MP * kBN;
-  if (p.S > 1) {
+  if (p.cluster) {
+    // ---- split-K inside a thread-block cluster: every k-slice's partial tile (and row statistics) stays in its CTA's shared
+    // memory; after one cluster barrier each CTA sums its share of the tile's 16-byte granules over the S slices in slice
+    // order (deterministic) through distributed shared memory and finishes them — no workspace round trip, no fence, no
+    // atomic ticket, and the epilogue of one tile is spread over S SMs.
+    if (tr0) B2_TR(g_gemv_tr, 7);
+    cluster_arrive();
+    cluster_wait();
+    if (tr0) B2_TR(g_gemv_tr, 8);
+    const uint32_t fs_a = smem_u32(fs), sinv_a = smem_u32(sinv);
+    if (p.norm_self) {
+      if (ctid < MP) {
+        float ss = 0.f;
+        for (int r = 0; r < p.S; ++r) ss += ld_dsmem_f(dsmem_addr(sinv_a + ctid * 4, r));
+        srs[ctid] = rsqrtf(ss * p.norm_inv_hidden + p.norm_eps);
+      }
+      named_bar_sync(1, kWarps * 32);
+    }
+    auto slice_sum = [&](int elem) {  // sum over the S slices of the 4 floats at fs[elem .. elem+3], slice order
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r0 = 0; r0 < p.S; r0 += 4) {
+        float4 b[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          b[r] = r0 + r < p.S ? ld_dsmem_f4(dsmem_addr(fs_a + elem * 4, r0 + r)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { a.x += b[r].x; a.y += b[r].y; a.z += b[r].z; a.w += b[r].w; }
+      }
+      return a;
+    };
+    const bool gather = p.comm_on || p.sumsq_out != nullptr;  // epilogues that need the whole tile in one CTA
+    if (!gather) {
+      if (p.act == B2_ACT_SWIGLU) {
+        for (int i = s + p.S * ctid; i < p.M * 16; i += p.S * kWarps * 32) {
+          const int m = i >> 4, cg = i & 15;
+          const int n = ng * 64 + cg * 4;
+          if (n >= p.N) continue;
+          const float4 gq = slice_sum(m * kBN + cg * 4), uq = slice_sum(m * kBN + 64 + cg * 4);
+          const float ra = p.norm_self ? p.alpha * srs[m] : p.alpha;
+          const float v[4] = {apply_act<B2_ACT_SILU>(gq.x * ra) * (uq.x * ra), apply_act<B2_ACT_SILU>(gq.y * ra) * (uq.y * ra),
+                              apply_act<B2_ACT_SILU>(gq.z * ra) * (uq.z * ra), apply_act<B2_ACT_SILU>(gq.w * ra) * (uq.w * ra)};
+          __nv_bfloat16* cp = p.C + (int64_t)m * p.ldc + n;
+          if (n + 3 < p.N && (reinterpret_cast<uintptr_t>(cp) & 7) == 0) {
+            *reinterpret_cast<uint2*>(cp) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (n + j < p.N) cp[j] = __float2bfloat16(v[j]);
+          }
+        }
+      } else {
+        for (int i = s + p.S * ctid; i < p.M * 32; i += p.S * kWarps * 32) {
+          const int m = i >> 5, c = (i & 31) * 4;
+          const int n = ng * kBN + c;
+          if (n >= p.N) continue;
+          const float4 q = slice_sum(m * kBN + c);
+          const float ra = p.norm_self ? p.alpha * srs[m] : p.alpha;
+          float v[4] = {q.x * ra, q.y * ra, q.z * ra, q.w * ra};
+          __nv_bfloat16* cp = p.C + (int64_t)m * p.ldc + n;
+          const __nv_bfloat16* rp = p.residual ? p.residual + (int64_t)m * p.ldc + n : nullptr;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (n + j < p.N) {
+              if (p.bias) v[j] += __bfloat162float(p.bias[n + j]);
+              v[j] = apply_act_rt(v[j], p.act);
+              if (rp) v[j] += __bfloat162float(rp[j]);
+            }
+          }
+          if (n + 3 < p.N && (reinterpret_cast<uintptr_t>(cp) & 7) == 0) {
+            *reinterpret_cast<uint2*>(cp) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (n + j < p.N) cp[j] = __float2bfloat16(v[j]);
+          }
+        }
+      }
+      if (tr0) B2_TR(g_gemv_tr, 10);
+      cluster_arrive();  // peers may still be reading this CTA's tile: stay resident until everybody is done
+      cluster_wait();
+      if (tr0) B2_TR(g_gemv_tr, 11);
+      return;
+    }
+    // gather: slice 0 collects the whole tile and runs the single-CTA epilogue below
+    if (s == 0) {
+      for (int i = ctid; i < p.M * 32; i += kWarps * 32) {
+        const float4 q = slice_sum(i * 4);
+        *reinterpret_cast<float4*>(fs + i * 4) = q;
+      }
+    }
+    cluster_arrive();
+    cluster_wait();
+    if (s != 0) return;
+  } else if (p.S > 1) {
     float* wsu = p.ws + ((size_t)ng * p.S + s) * MPK;
     for (int i = ctid * 4; i < p.M * kBN; i += kWarps * 32 * 4)
       *reinterpret_cast<float4*>(wsu + i) = *reinterpret_cast<const float4*>(fs + i);
+    float* wsq = p.ws + (size_t)p.NG * p.S * MPK;  // [NG][S][MP] sum x^2 of each k-slice (self-contained norm)
+    if (p.norm_self && ctid < p.M) wsq[((size_t)ng * p.S + s) * MP + ctid] = sinv[ctid];
     __threadfence();
     named_bar_sync(1, kWarps * 32);
     if (tr0) B2_TR(g_gemv_tr, 7);
@@ -358,6 +512,12 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
     // fixed-order sum over the S partials (deterministic); loads are issued 8 at a time so the L2 round
     // trips overlap instead of serialising behind the adds
     const float* wsg = p.ws + (size_t)ng * p.S * MPK;
+    float ssq_l = 0.f;  // lane s holds slice s of row (warp, warp + 8): one round trip, overlapped with the tile loads below
+    float ssq_h = 0.f;
+    if (p.norm_self) {
+      if (lane < p.S && warp < p.M) ssq_l = __ldcg(wsq + ((size_t)ng * p.S + lane) * MP + warp);
+      if (lane < p.S && warp + kWarps < p.M) ssq_h = __ldcg(wsq + ((size_t)ng * p.S + lane) * MP + warp + kWarps);
+    }
     for (int i = ctid * 4; i < p.M * kBN; i += kWarps * 32 * 4) {
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int s0 = 0; s0 < p.S; s0 += 8) {
@@ -371,19 +531,35 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
       }
       *reinterpret_cast<float4*>(fs + i) = a;
     }
+    if (p.norm_self) {  // S <= 32 slices, MP <= 16 rows
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ssq_l += __shfl_xor_sync(0xffffffffu, ssq_l, o);
+        ssq_h += __shfl_xor_sync(0xffffffffu, ssq_h, o);
+      }
+      if (lane == 0) {
+        sinv[warp] = ssq_l;
+        if (MP > kWarps) sinv[warp + kWarps] = ssq_h;
+      }
+    }
     if (ctid == 0) p.counters[ng] = 0;  // re-arm for the next launch / graph replay
     named_bar_sync(1, kWarps * 32);
     if (ng == 0 && ctid == 0) B2_TR(g_gemv_tr, 10);
   }
 
-  // ---- final: alpha, bias, activation, residual, bf16 store (coalesced along n)
+  if (p.norm_self && !p.cluster) {  // sum x^2 -> 1/rms, one thread per row (the cluster path already has it)
+    if (ctid < MP) srs[ctid] = rsqrtf(sinv[ctid] * p.norm_inv_hidden + p.norm_eps);
+    named_bar_sync(1, kWarps * 32);
+  }
+  // ---- final: alpha (x 1/rms of the row), bias, activation, residual, bf16 store (coalesced along n)
   if (p.act == B2_ACT_SWIGLU) {  // tile = [64 gate | 64 up] channels of n in [64*ng, 64*ng+64): out = silu(gate) * up
     for (int i = ctid; i < p.M * 32; i += kWarps * 32) {
       const int m = i >> 5, np = i & 31;
       const int n = ng * 64 + np * 2;
       if (n >= p.N) continue;
-      const float g0 = fs[m * kBN + np * 2] * p.alpha, g1 = fs[m * kBN + np * 2 + 1] * p.alpha;
-      const float u0 = fs[m * kBN + 64 + np * 2] * p.alpha, u1 = fs[m * kBN + 64 + np * 2 + 1] * p.alpha;
+      const float ra = p.norm_self ? p.alpha * srs[m] : p.alpha;
+      const float g0 = fs[m * kBN + np * 2] * ra, g1 = fs[m * kBN + np * 2 + 1] * ra;
+      const float u0 = fs[m * kBN + 64 + np * 2] * ra, u1 = fs[m * kBN + 64 + np * 2 + 1] * ra;
       const float v0 = apply_act<B2_ACT_SILU>(g0) * u0, v1 = apply_act<B2_ACT_SILU>(g1) * u1;
       __nv_bfloat16* cp = p.C + (int64_t)m * p.ldc + n;
       if ((n + 1) < p.N && ((reinterpret_cast<uintptr_t>(cp) & 3) == 0)) *reinterpret_cast<uint32_t*>(cp) = pack_bf16x2(v0, v1);
@@ -468,7 +644,8 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
     const int m = i >> 6, np = i & 63;
     const int n = ng * kBN + np * 2;
     if (n >= p.N) continue;
-    float v0 = fs[m * kBN + np * 2] * p.alpha, v1 = fs[m * kBN + np * 2 + 1] * p.alpha;
+    const float ra = p.norm_self ? p.alpha * srs[m] : p.alpha;
+    float v0 = fs[m * kBN + np * 2] * ra, v1 = fs[m * kBN + np * 2 + 1] * ra;
     const bool has1 = (n + 1) < p.N;
     if (p.bias) {
       v0 += __bfloat162float(p.bias[n]);
@@ -617,6 +794,7 @@ using namespace b2;
 struct Plan {
   bool valid = false;
   int S = 1, xt = 1, smem = 0, quanta = 1, nst_log2 = 2;
+  bool cluster = false;  // the S k-slices of a tile form a thread-block cluster (DSMEM reduction)
 };
 
 struct b2_gemm_wq {
@@ -681,22 +859,26 @@ static int make_plan(b2_gemm_wq* h, int mti) {
   const int sms = sm_count();
   gemm_kernel_t kern = pick_kernel(h->d.wbits, grouped, mt);
   const int ring_kb = env_int("B2_GEMM_RING_KB", 32);
-  int nst_log2 = 1;
-  while ((2 << nst_log2) * stage_bytes_of(h->d.wbits) <= ring_kb * 1024) ++nst_log2;
-  const int nstage = 1 << nst_log2;
+  auto log2_stages = [&](int kb) {
+    int l = 1;
+    while ((2 << l) * stage_bytes_of(h->d.wbits) <= kb * 1024) ++l;
+    return l;
+  };
+  int nst_log2 = log2_stages(ring_kb);
   const int tps = kStageBytes / tile_bytes_of(h->d.wbits) > 0 ? kStageBytes / tile_bytes_of(h->d.wbits) : 1;
   const int xq = gt > tps ? gt : tps;  // chunk granularity (gt and tps are powers of two)
   const int x_budget = env_int("B2_GEMM_XBYTES", 20 * 1024);
   // activation chunk: as many k-tiles as fit the budget, a multiple of the quant group
-  int xt_cap = (x_budget / MP - 16) / 128;
+  int xt_cap = (x_budget / (MP + 1) - 16) / 128;  // MP activation rows + the gamma slice
   xt_cap = xt_cap / xq * xq;
   if (xt_cap < xq) xt_cap = xq;
-  auto smem_for = [&](int xt) {
+  auto smem_for = [&](int xt, int nl2) {
     const int gpc = grouped ? xt / gt : 1;
-    return nstage * stage_bytes_of(h->d.wbits) + MP * (xt * 128 + 16) + MP * kBN * 4 + MP * gpc * 4 + MP * 4 + 16 + 8 + nstage * 16 + 64;
+    return (1 << nl2) * stage_bytes_of(h->d.wbits) + (MP + 1) * (xt * 128 + 16) + MP * kBN * 4 + MP * gpc * 4 + 2 * MP * 4 + 16 + 8 +
+           (1 << nl2) * 16 + 16 + 64;
   };
   // first guess occupancy with the cap, derive S, then shrink xt to what a unit really needs
-  int smem = smem_for(xt_cap);
+  int smem = smem_for(xt_cap, nst_log2);
   B2_CUDA_TRY(raise_smem_limit(kern, smem));
   int occ = 1;
   B2_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
@@ -712,13 +894,51 @@ static int make_plan(b2_gemm_wq* h, int mti) {
   if (S < 1) S = 1;
   const int force = env_int("B2_GEMM_FORCE_SPLIT", 0);
   if (force > 0) S = force < quanta ? force : quanta;
+  if (S > 32) S = 32;  // the reducer reads one k-slice statistic per lane
+  // ---- split-K inside thread-block clusters (the default when it keeps enough CTAs in flight): S in {2, 4, 8} slices of a
+  // tile form one cluster, the partial tiles meet in distributed shared memory.  Fewer, fatter CTAs than the global
+  // split (<= 8 slices), so the ring grows to keep the same number of weight bytes in flight.
+  bool cluster = false;
+  if (env_int("B2_GEMM_CLUSTER", 1) && force <= 0 && S > 1) {
+    const int cmax = env_int("B2_GEMM_CLUSTER_MAX", 8);  // 16 (non-portable, opt-in) measured no better: o_proj 7.3 vs 6.4 us
+    int sc = 2;
+    while (sc * 2 <= S && sc * 2 <= cmax) sc *= 2;
+    if (sc > 8) B2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    while (sc > 1 && !cluster) {
+      if (h->NG * sc * 4 < sms * 3) break;  // too few CTAs to pull the HBM bandwidth: keep the wide global split
+      const int nl2 = h->NG * sc <= 2 * sms ? log2_stages(env_int("B2_GEMM_CLUSTER_RING_KB", 64)) : nst_log2;
+      const int sm_c = smem_for(xt_cap, nl2);
+      B2_CUDA_TRY(raise_smem_limit(kern, sm_c));
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(h->NG * sc);
+      cfg.blockDim = dim3(kThreads);
+      cfg.dynamicSmemBytes = sm_c;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = sc;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int ncl = 0;
+      if (cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg) == cudaSuccess && ncl >= h->NG) {  // one wave
+        cluster = true;
+        S = sc;
+        nst_log2 = nl2;
+      } else {
+        (void)cudaGetLastError();
+        sc >>= 1;
+      }
+    }
+  }
   const int unit_tiles = ((quanta + S - 1) / S) * gt;
   int xt = unit_tiles < xt_cap ? unit_tiles : xt_cap;
   xt = (xt + xq - 1) / xq * xq;
   pl.S = S;
   pl.xt = xt;
   pl.nst_log2 = nst_log2;
-  pl.smem = smem_for(xt);
+  pl.cluster = cluster;
+  pl.smem = smem_for(xt, nst_log2);
   pl.quanta = quanta;
   pl.valid = true;
   return B2_OK;
@@ -886,8 +1106,8 @@ size_t b2_gemm_wq_workspace_bytes(b2_gemm_wq_t h, int M) {
   const int mti = mt_index_for(mc);
   if (make_plan(h, mti) != B2_OK) return 0;
   const Plan& pl = h->plans[mti];
-  if (pl.S <= 1) return 16;
-  return (size_t)h->NG * pl.S * (8 << mti) * kBN * sizeof(float) + 16;
+  if (pl.S <= 1 || pl.cluster) return 16;
+  return (size_t)h->NG * pl.S * (8 << mti) * (kBN + 1) * sizeof(float) + 16;  // partial tiles + per-slice sum x^2
 }
 
 size_t b2_gemm_wq_algo_bytes(b2_gemm_wq_t h, int M) {
@@ -972,7 +1192,10 @@ static int run_impl(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, int64_t
                     const void* residual, int activation, float alpha, void* workspace, size_t workspace_bytes,
                     const b2_gemm_fuse* fuse, const CommDev* comm, void* stream_) {
   if (!h || !A || !C || M <= 0) return B2_ERR_PARAM;
-  const bool fused = fuse && (fuse->norm_sumsq || fuse->sumsq_out);
+  const bool norm_self = fuse && !fuse->norm_sumsq && fuse->norm_gamma;
+  const bool fused = fuse && (fuse->norm_sumsq || fuse->sumsq_out || norm_self);
+  if (norm_self && (fuse->norm_hidden != h->d.K || comm)) return B2_ERR_PARAM;
+  if (norm_self && (reinterpret_cast<uintptr_t>(fuse->norm_gamma) & 15)) return B2_ERR_UNSUPPORTED;  // bulk-copied by slices  // the row statistics span exactly this GEMM's K
   if (fused && (M > 16 || h->pair && fuse->sumsq_out)) return B2_ERR_UNSUPPORTED;
   if (fuse && fuse->norm_sumsq && (!fuse->norm_gamma || fuse->norm_parts <= 0 || fuse->norm_hidden <= 0)) return B2_ERR_PARAM;
   if (!h->packed) return B2_ERR_RUNTIME;
@@ -1039,7 +1262,7 @@ splitk:
     const int mti = mt_index_for(mc);
     if (int st = make_plan(h, mti)) return st;
     const Plan& pl = h->plans[mti];
-    if (pl.S > 1 && !workspace) return B2_ERR_PARAM;
+    if (pl.S > 1 && !pl.cluster && !workspace) return B2_ERR_PARAM;
     GemmParams p;
     p.packed = (const uint8_t*)h->packed;
     p.sz = h->sz;
@@ -1061,6 +1284,8 @@ splitk:
     p.norm_sumsq = fuse ? fuse->norm_sumsq : nullptr;
     p.norm_gamma = fuse ? (const __nv_bfloat16*)fuse->norm_gamma : nullptr;
     p.norm_parts = fuse ? fuse->norm_parts : 0;
+    p.norm_self = norm_self ? 1 : 0;
+    p.cluster = pl.cluster ? 1 : 0;
     p.norm_inv_hidden = fuse && fuse->norm_hidden > 0 ? 1.0f / (float)fuse->norm_hidden : 0.f;
     p.norm_eps = fuse ? fuse->norm_eps : 0.f;
     p.sumsq_out = fuse ? fuse->sumsq_out : nullptr;
@@ -1068,7 +1293,8 @@ splitk:
     if (comm) p.comm = *comm;
     else memset(&p.comm, 0, sizeof(p.comm));
     gemm_kernel_t kern = pick_kernel(h->d.wbits, grouped, 1 << mti);
-    cudaError_t e = launch(kern, dim3(h->NG * pl.S), dim3(kThreads), (size_t)pl.smem, stream, true, p);
+    cudaError_t e = pl.cluster ? launch_cluster(kern, dim3(h->NG * pl.S), dim3(kThreads), (size_t)pl.smem, stream, true, (unsigned)pl.S, p)
+                               : launch(kern, dim3(h->NG * pl.S), dim3(kThreads), (size_t)pl.smem, stream, true, p);
     if (e != cudaSuccess) {
       set_last_error("wq_gemm launch", e);
       return B2_ERR_CUDA;

@@ -78,7 +78,7 @@ class GemmWQ:
         return lib.b2_gemm_wq_sumsq_parts(self.h)
 
     def __call__(self, a, ws, out=None, act=ACT_NONE, alpha=1.0, residual=None, norm_in=None, sumsq_out=None):
-        """norm_in = (sumsq [parts, M] fp32, gamma [K] bf16, hidden, eps): fused RMSNorm prologue;
+        """norm_in = (sumsq [parts, M] fp32 or None, gamma [K] bf16, hidden, eps): fused RMSNorm prologue;
         sumsq_out [sumsq_parts(), M] fp32: per-tile row sums of squares of the output (for the next op's norm_in)."""
         if self.pair:
             act = _lib.ACT_SWIGLU
@@ -95,9 +95,9 @@ class GemmWQ:
             return out
         f = GemmFuse()
         if norm_in is not None:
-            ss, gamma, hidden, eps = norm_in
-            f.norm_sumsq, f.norm_gamma = ss.data_ptr(), gamma.data_ptr()
-            f.norm_parts, f.norm_hidden, f.norm_eps = ss.shape[0], int(hidden), float(eps)
+            ss, gamma, hidden, eps = norm_in   # ss None: the GEMV takes the row statistics itself (hidden == K)
+            f.norm_sumsq, f.norm_gamma = (ss.data_ptr() if ss is not None else None), gamma.data_ptr()
+            f.norm_parts, f.norm_hidden, f.norm_eps = (ss.shape[0] if ss is not None else 0), int(hidden), float(eps)
         if sumsq_out is not None:
             f.sumsq_out = sumsq_out.data_ptr()
         check(lib.b2_gemm_wq_run_fused(self.h, _ptr(a), lda, _ptr(out), ldc, M, _ptr(self.bias), _ptr(residual), act,

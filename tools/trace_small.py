@@ -18,7 +18,8 @@ st = model.DecodeStack(model.QWEN2_7B, B, ctx + 64, wbits=wbits, kv=kv, layers=4
 st.set_context(ctx)
 ws = st.ws
 GEMV_EV = ["entry", "barriers+sync", "first TMA issued", "pdl_wait done", "activations staged", "first weights landed", "main loop end",
-           "partial written+fence", "atomic done", "last CTA: reduce start", "last CTA: reduce end", "store done (ng 0)"]
+           "partial written+fence", "atomic done", "last CTA: reduce start", "last CTA: reduce end", "store done (ng 0)",
+           "x copies issued", "x landed", "x pass done"]
 ATTN_EV = ["entry", "pdl_wait done", "decomposition done", "Q fragments", "first tile landed", "tile loop end", "cta merge done",
            "partial fenced", "l1 merge start", "l1 merge end", "final merge start", "final merge end"]
 
@@ -54,6 +55,13 @@ for key in ("qkv", "o", "gateup", "down"):
     fns = [(lambda L=L: L[key](src, ws, out=dst)) for L in st.layers]
     us = timed(fns)
     print("%-7s B=%d  %.2f us/launch   trace(ns): %s" % (key, B, us, read("b2_debug_trace_gemv", GEMV_EV)), flush=True)
+if B <= 16:  # the self-contained RMSNorm form of the column-parallel GEMVs
+    H = st.cfg.hidden
+    for key, gk in (("qkv", "g1"), ("gateup", "g2")):
+        dst = io[key][1]
+        fns = [(lambda L=L: L[key](st.x, ws, out=dst, norm_in=(None, L[gk], H, st.cfg.eps))) for L in st.layers]
+        us = timed(fns)
+        print("%-7s+norm B=%d  %.2f us/launch   trace(ns): %s" % (key, B, us, read("b2_debug_trace_gemv", GEMV_EV)), flush=True)
 fns = [(lambda L=L: st.attn(st.q, L["cache"], st.lens_new, st.max_len, ws, out=st.ao)) for L in st.layers]
 us = timed(fns)
 print("attn    B=%d ctx=%d kv=%s  %.2f us/launch   trace(ns): %s" % (B, ctx, kv, us, read("b2_debug_trace_attn", ATTN_EV)), flush=True)
