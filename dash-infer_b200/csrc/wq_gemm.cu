@@ -808,6 +808,7 @@ struct b2_gemm_wq {
   unsigned* counters = nullptr;
   Plan plans[3];  // MT = 1, 2, 4
   int tc_S = 0;   // split-K of the tcgen05 path (0 = not planned)
+  int tc_S2 = 0;  // same for the two-CTAs-per-SM variant (int4, bf16 activations)
   bool pair = false;  // gate/up pair image (SwiGLU epilogue): physical channels = 2 * N
   int device = 0;
 };
@@ -1085,21 +1086,30 @@ static int make_tc_plan(b2_gemm_wq* h) {
   if (h->tc_S > 0) return B2_OK;
   B2_CUDA_TRY(tc_configure(h->d.wbits));
   const int ctas = env_int("B2_GEMM_TC_CTAS_PER_SM", 1);
-  const int slots = ctas * sm_count();
-  int S = slots / h->NG;
-  if (S > h->KT / 4) S = h->KT / 4;
-  const int smax = env_int("B2_GEMM_TC_MAX_SPLIT", 6);
-  if (S > smax) S = smax;
-  if (S < 1) S = 1;
-  h->tc_S = S;
+  auto split_for = [&](int slots, int smax) {
+    int S = slots / h->NG;
+    if (S > h->KT / 4) S = h->KT / 4;
+    if (S > smax) S = smax;
+    return S < 1 ? 1 : S;
+  };
+  h->tc_S = split_for(ctas * sm_count(), env_int("B2_GEMM_TC_MAX_SPLIT", 6));
+  h->tc_S2 = split_for(env_int("B2_GEMM_TC_DUAL_SLOTS", 2) * sm_count(), env_int("B2_GEMM_TC_MAX_SPLIT2", 8));
   return B2_OK;
+}
+
+// two CTAs per SM on the tcgen05 path: int4 weights with bf16 activations (B2_GEMM_TC_DUAL=0: one 200 KB CTA per SM)
+static bool tc_dual(const b2_gemm_wq* h) {
+  static const int on = env_int("B2_GEMM_TC_DUAL", 1);  // 2: every int4 shape, 1: shapes with >= 2 units per SM without split-K
+  if (!on || h->d.wbits != 4) return false;
+  return on >= 2 || h->NG >= 2 * sm_count();
 }
 
 size_t b2_gemm_wq_workspace_bytes(b2_gemm_wq_t h, int M) {
   if (!h || M <= 0) return 0;
   if (use_tc(h, M)) {
     if (make_tc_plan(h) != B2_OK) return 0;
-    return h->tc_S <= 1 ? 16 : (size_t)h->NG * h->tc_S * kTcMaxM * kBN * sizeof(float) + 16;
+    const int sm = h->tc_S > h->tc_S2 ? h->tc_S : h->tc_S2;  // the fp8 entry point keeps the one-CTA-per-SM split
+    return sm <= 1 ? 16 : (size_t)h->NG * sm * kTcMaxM * kBN * sizeof(float) + 16;
   }
   const int rpl = rows_per_launch(h);
   const int mc = M > rpl ? rpl : M;
@@ -1209,9 +1219,12 @@ static int run_impl(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, int64_t
   const bool grouped = h->group_tiles > 0;
   if (use_tc(h, M) && !comm) {  // decode batches 17..: tcgen05 path, 64 rows per launch
     if (int st = make_tc_plan(h)) return st;
-    if (h->tc_S > 1 && !workspace) return B2_ERR_PARAM;
+    const bool dual = tc_dual(h);
+    const int tcs = dual ? h->tc_S2 : h->tc_S;
+    if (tcs > 1 && !workspace) return B2_ERR_PARAM;
     for (int m0 = 0; m0 < M; m0 += kTcMaxM) {
       TcLaunch a;
+      a.dual = dual;
       a.packed = (const uint8_t*)h->packed; a.sz = h->sz;
       a.A = (const __nv_bfloat16*)A + (int64_t)m0 * lda; a.lda = lda;
       a.C = (__nv_bfloat16*)C + (int64_t)m0 * ldc; a.ldc = ldc;
@@ -1219,7 +1232,7 @@ static int run_impl(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, int64_t
       a.residual = residual ? (const __nv_bfloat16*)residual + (int64_t)m0 * ldc : nullptr;
       a.ws = (float*)workspace; a.counters = h->counters;
       a.M = (M - m0) > kTcMaxM ? kTcMaxM : (M - m0);
-      a.N = h->d.N; a.K = h->d.K; a.Np = h->Np; a.KT = h->KT; a.NG = h->NG; a.S = h->tc_S;
+      a.N = h->d.N; a.K = h->d.K; a.Np = h->Np; a.KT = h->KT; a.NG = h->NG; a.S = tcs;
       a.act = activation; a.alpha = alpha;
       a.group_tiles = h->group_tiles;
       cudaError_t e = tc_launch(h->d.wbits, a, stream);

@@ -38,6 +38,7 @@ struct TcLaunch {
   const float* a_scale = nullptr;    // != NULL: A is fp8-e4m3 in the b2 fp8 activation layout (lda in bytes)
   const float* tile_sums = nullptr;  // [M][KT] sums of the quantized activations per 64-k tile
   int group_tiles = 0;               // > 0: sub-channel weights, k-tiles per quantization group (sz is [G][Np])
+  bool dual = false;                 // two CTAs per SM (int4 weights, bf16 activations): half-depth stages, 256 TMEM columns
 };
 // GEMV without global split-K (wq_gemv2.cu)
 struct Gemv2Launch {
@@ -62,7 +63,7 @@ bool gemv2_plan(const Gemv2Launch& a, Gemv2Plan* plan);   // false: use the spli
 cudaError_t gemv2_launch(const Gemv2Launch& a, const Gemv2Plan& plan, cudaStream_t stream);
 
 constexpr int kTcMaxM = 64;  // batch rows per tcgen05 launch
-int tc_smem_bytes(int wbits);
+int tc_smem_bytes(int wbits, bool dual);
 cudaError_t tc_configure(int wbits);
 cudaError_t tc_launch(int wbits, const TcLaunch& a, cudaStream_t stream);
 

@@ -166,15 +166,21 @@ struct TcParams {
 // in bf16, then ONE fused multiply-add per two weights: w = (q - 8) * s + (8 - z) * s, rounded to bf16 once — which is what
 // the reference's kernels (dequant in FT, gemm_lowp_utils.cuh:28-47) and its CPU path (weights stored in the model dtype)
 // feed their GEMMs with; the accumulator then needs no zero-point term and no row sums.
-template <int WBITS, bool MULTI, bool A8 = false, bool GROUPED = false>
-__global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap amap) {
+// DUAL: two CTAs per SM (int4, bf16 activations).  A stage is half as deep (k128: 8 KB of weights, 16 KB of activations, 64
+// TMEM columns of dequantized A), so a CTA needs 97 KB of shared memory and 256 TMEM columns; the fixed part of a unit —
+// prologue, pipeline fill, accumulator read-out, split-K hand-off, epilogue (6.4 of 17.6 us on the gate projection,
+// profiles/r2_timelines.md) — overlaps the main loop of the CTA next to it instead of idling the SM.
+template <int WBITS, bool MULTI, bool A8 = false, bool GROUPED = false, bool DUAL = false>
+__global__ void __launch_bounds__(kTcThreads, DUAL ? 2 : 1) wq_gemm_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap amap) {
   constexpr int TILE_BYTES = WBITS == 4 ? 4096 : (WBITS == 8 ? 8192 : 16384);
   constexpr int NCH = WBITS == 4 ? 2 : (WBITS == 8 ? 4 : 8);  // 16B chunks per row per k-tile
   constexpr int NSW = WBITS == 16 ? 4 : kTcNSW;               // weight stages (bf16: 32 KB each)
   // k-tiles per pipeline stage (k256 for W4, k128 for W8): one stage = 16 KB of weights = 16 tcgen05.mma per
   // commit / barrier round trip of the issuing thread (that round trip costs ~400 clocks, an MMA 45)
-  constexpr int TPS = WBITS == 4 ? 4 : 2;
+  constexpr int TPS = WBITS == 4 ? (DUAL ? 2 : 4) : 2;
+  constexpr int TMEM_COLS = DUAL ? 256 : kTcTmemCols;
   static_assert(!A8 || WBITS == 4, "fp8 activations: int4 weights only");
+  static_assert(!DUAL || (WBITS == 4 && !A8), "two CTAs per SM: int4 weights, bf16 activations");
   static_assert(!GROUPED || (!A8 && WBITS != 16), "sub-channel weights: bf16 activations, int4 / int8");
   const int XTILE_LD = p.nm * 128;             // bytes the TMA writes per activation tile (the tile slot stays 64 rows)
   constexpr int ACOLS = A8 ? 16 : (WBITS == 8 ? 64 : 32);  // TMEM columns of dequantized A per k-tile (int8: lo and hi planes)
@@ -212,7 +218,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
     fence_mbar_init();
   }
   if (warp == 1) {  // TMEM allocation (this warp also frees it)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTcTmemCols) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -705,7 +711,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) wq_gemm_tc_kernel(const TcParam
   if (tid == 0) { TC_TRACE(7, 3); TC_GT(2); }
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTcTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -720,8 +726,8 @@ extern "C" int b2_debug_tc_gt(unsigned long long* host_out, unsigned* launches) 
 }
 #endif
 
-int tc_smem_bytes(int wbits) {
-  const int tps = wbits == 4 ? 4 : 2;
+int tc_smem_bytes(int wbits, bool dual) {
+  const int tps = wbits == 4 ? (dual ? 2 : 4) : 2;
   const int wstage = tps * (wbits == 4 ? 4096 : (wbits == 8 ? 8192 : 16384));
   const int nsw = wbits == 16 ? 4 : kTcNSW;
   return 1024 + kTcNSX * tps * kTcXTile + nsw * wstage + kTcNM * 4 + 96 * 8 + 64;  // barrier block: 25 barriers, TMEM slot, 64 scales
@@ -729,8 +735,11 @@ int tc_smem_bytes(int wbits) {
 
 cudaError_t tc_configure(int wbits) {
   cudaError_t e = cudaSuccess;
-  auto cfg = [&](auto kern) { if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(wbits)); };
+  auto cfg = [&](auto kern) { if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(wbits, false)); };
+  auto cfg2 = [&](auto kern) { if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(wbits, true)); };
   if (wbits == 4) {
+    cfg2(wq_gemm_tc_kernel<4, false, false, false, true>); cfg2(wq_gemm_tc_kernel<4, true, false, false, true>);
+    cfg2(wq_gemm_tc_kernel<4, false, false, true, true>); cfg2(wq_gemm_tc_kernel<4, true, false, true, true>);
     cfg(wq_gemm_tc_kernel<4, false>); cfg(wq_gemm_tc_kernel<4, true>); cfg(wq_gemm_tc_kernel<4, false, true>); cfg(wq_gemm_tc_kernel<4, true, true>);
     cfg(wq_gemm_tc_kernel<4, false, false, true>); cfg(wq_gemm_tc_kernel<4, true, false, true>);
   }
@@ -788,9 +797,18 @@ cudaError_t tc_launch(int wbits, const TcLaunch& a, cudaStream_t stream) {
   // persistent: one CTA per SM walks the (n-group, k-split) units; B2_GEMM_TC_PERSIST=0 launches one CTA per unit
   static const int persist = [] { const char* e = getenv("B2_GEMM_TC_PERSIST"); return e ? atoi(e) : 1; }();
   const int units = a.NG * a.S;
-  const int grid = (persist && units > sm_count()) ? sm_count() : units;
+  const bool dual = a.dual && wbits == 4 && !a8;
+  const int cap = (dual ? 2 : 1) * sm_count();
+  const int grid = (persist && units > cap) ? cap : units;
   const bool multi = units > grid;
-  const size_t smem = (size_t)tc_smem_bytes(wbits);
+  const size_t smem = (size_t)tc_smem_bytes(wbits, dual);
+  if (dual) {
+    if (a.group_tiles > 0)
+      return multi ? launch(wq_gemm_tc_kernel<4, true, false, true, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap)
+                   : launch(wq_gemm_tc_kernel<4, false, false, true, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap);
+    return multi ? launch(wq_gemm_tc_kernel<4, true, false, false, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap)
+                 : launch(wq_gemm_tc_kernel<4, false, false, false, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap);
+  }
   if (a8) {
     if (wbits != 4) return cudaErrorNotSupported;
     return multi ? launch(wq_gemm_tc_kernel<4, true, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap)
