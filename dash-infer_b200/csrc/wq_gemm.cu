@@ -1203,11 +1203,26 @@ static int run_impl(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, int64_t
                     const b2_gemm_fuse* fuse, const CommDev* comm, void* stream_) {
   if (!h || !A || !C || M <= 0) return B2_ERR_PARAM;
   const bool norm_self = fuse && !fuse->norm_sumsq && fuse->norm_gamma;
-  const bool fused = fuse && (fuse->norm_sumsq || fuse->sumsq_out || norm_self);
-  if (norm_self && (fuse->norm_hidden != h->d.K || comm)) return B2_ERR_PARAM;
-  if (norm_self && (reinterpret_cast<uintptr_t>(fuse->norm_gamma) & 15)) return B2_ERR_UNSUPPORTED;  // bulk-copied by slices  // the row statistics span exactly this GEMM's K
-  if (fused && (M > 16 || h->pair && fuse->sumsq_out)) return B2_ERR_UNSUPPORTED;
-  if (fuse && fuse->norm_sumsq && (!fuse->norm_gamma || fuse->norm_parts <= 0 || fuse->norm_hidden <= 0)) return B2_ERR_PARAM;
+  const bool fused = fuse && (fuse->norm_sumsq || fuse->sumsq_out || norm_self || fuse->xg_out);
+  if (fused && use_tc(h, M) && !comm) {
+    // ---- batches >= 17: the hand-off form only (pre-scaled activations in; scaled copy + statistics out)
+    const bool cons = fuse->norm_sumsq != nullptr, prod = fuse->xg_out != nullptr;
+    if (norm_self || (cons && fuse->norm_gamma) || (fuse->sumsq_out && !prod)) return B2_ERR_UNSUPPORTED;
+    if (cons && (fuse->norm_parts <= 0 || fuse->norm_hidden <= 0)) return B2_ERR_PARAM;
+    if (prod) {
+      if (!fuse->sumsq_out || !fuse->gamma_out || h->pair || activation != B2_ACT_NONE) return B2_ERR_PARAM;
+      // the statistics come out of the vectorised residual epilogue: 8-byte aligned rows everywhere
+      if ((h->d.N & 3) || (ldc & 3) || (fuse->ldxg & 3) || (reinterpret_cast<uintptr_t>(C) & 7) ||
+          (reinterpret_cast<uintptr_t>(fuse->xg_out) & 7) || (reinterpret_cast<uintptr_t>(fuse->gamma_out) & 7) ||
+          (residual && (reinterpret_cast<uintptr_t>(residual) & 7)) || (bias && (reinterpret_cast<uintptr_t>(bias) & 7)))
+        return B2_ERR_UNSUPPORTED;
+    }
+  } else {
+    if (norm_self && (fuse->norm_hidden != h->d.K || comm)) return B2_ERR_PARAM;  // the row statistics span exactly this GEMM's K
+    if (norm_self && (reinterpret_cast<uintptr_t>(fuse->norm_gamma) & 15)) return B2_ERR_UNSUPPORTED;  // bulk-copied by slices
+    if (fused && (M > 16 || (h->pair && fuse->sumsq_out) || fuse->xg_out)) return B2_ERR_UNSUPPORTED;
+    if (fuse && fuse->norm_sumsq && (!fuse->norm_gamma || fuse->norm_parts <= 0 || fuse->norm_hidden <= 0)) return B2_ERR_PARAM;
+  }
   if (!h->packed) return B2_ERR_RUNTIME;
   if (M > h->d.max_m) return B2_ERR_LIMIT;
   if (h->pair != (activation == B2_ACT_SWIGLU)) return B2_ERR_PARAM;  // paired image <=> SwiGLU epilogue
@@ -1235,6 +1250,18 @@ static int run_impl(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, int64_t
       a.N = h->d.N; a.K = h->d.K; a.Np = h->Np; a.KT = h->KT; a.NG = h->NG; a.S = tcs;
       a.act = activation; a.alpha = alpha;
       a.group_tiles = h->group_tiles;
+      if (fused) {
+        a.norm_ld = M;
+        if (fuse->norm_sumsq) {
+          a.norm_sumsq = fuse->norm_sumsq + m0; a.norm_parts = fuse->norm_parts;
+          a.norm_inv_hidden = 1.0f / (float)fuse->norm_hidden; a.norm_eps = fuse->norm_eps;
+        }
+        if (fuse->xg_out) {
+          a.sumsq_out = fuse->sumsq_out + m0;
+          a.xg_out = (__nv_bfloat16*)fuse->xg_out + (int64_t)m0 * fuse->ldxg;
+          a.gamma_out = (const __nv_bfloat16*)fuse->gamma_out; a.ldxg = fuse->ldxg;
+        }
+      }
       cudaError_t e = tc_launch(h->d.wbits, a, stream);
       if (e != cudaSuccess) {
         set_last_error("wq_gemm_tc launch", e);

@@ -39,6 +39,16 @@ struct TcLaunch {
   const float* tile_sums = nullptr;  // [M][KT] sums of the quantized activations per 64-k tile
   int group_tiles = 0;               // > 0: sub-channel weights, k-tiles per quantization group (sz is [G][Np])
   bool dual = false;                 // two CTAs per SM (int4 weights, bf16 activations): half-depth stages, 256 TMEM columns
+  // RMSNorm hand-off between GEMMs (b2_gemm_fuse, batches >= 17).  Consumer: A holds bf16(x * gamma); the result rows are
+  // scaled by rsqrt(sum_p norm_sumsq[p * norm_ld + m] / hidden + eps).  Producer: besides C it writes xg = bf16(C * gamma_out)
+  // and, per 128-channel tile, the sum of squares of every stored row.
+  const float* norm_sumsq = nullptr;
+  int norm_parts = 0, norm_ld = 0;
+  float norm_inv_hidden = 0.f, norm_eps = 0.f;
+  float* sumsq_out = nullptr;        // [NG][norm_ld]
+  __nv_bfloat16* xg_out = nullptr;   // [M, ldxg]
+  const __nv_bfloat16* gamma_out = nullptr;
+  int64_t ldxg = 0;
 };
 // GEMV without global split-K (wq_gemv2.cu)
 struct Gemv2Launch {

@@ -145,6 +145,14 @@ struct TcParams {
   // fp8 activations (A8 instantiation): per-token scale [M] and per-(row, 64-k tile) sums of the quantized values [M][KT]
   const float* a_scale;
   const float* tile_sums;
+  // RMSNorm hand-off (see TcLaunch)
+  const float* norm_sumsq;
+  int norm_parts, norm_ld;
+  float norm_inv_hidden, norm_eps;
+  float* sumsq_out;
+  __nv_bfloat16* xg_out;
+  const __nv_bfloat16* gamma_out;
+  int64_t ldxg;
   int nm;           // MMA N (batch columns): 64, or 32 when M <= 32 (half the tensor-pipe time and activation traffic)
   int group_tiles;  // GROUPED instantiation: k-tiles per quantization group; sz is [G][Np]
   int dbg;  // ablation bitmask, only honoured when compiled with -DB2_TC_ABLATE (tools/tc_ablate.py)
@@ -379,6 +387,13 @@ __global__ void __launch_bounds__(kTcThreads, DUAL ? 2 : 1) wq_gemm_tc_kernel(co
         ascale[xt] = 0.f;
       }
     }
+    if (!A8 && p.norm_sumsq) {  // the producer's per-tile row statistics -> 1/rms per row, applied at the accumulator read-out
+      pdl_wait();
+      float ss = 0.f;
+      if (xt < p.M)
+        for (int i = 0; i < p.norm_parts; ++i) ss += __ldcg(p.norm_sumsq + (size_t)i * p.norm_ld + xt);
+      ascale[xt] = rsqrtf(ss * p.norm_inv_hidden + p.norm_eps);
+    }
     for (int st = 0; st < nst; ++st) {
       const int g = gbase + st;
       const int slot = g % kTcNSX;
@@ -547,6 +562,17 @@ __global__ void __launch_bounds__(kTcThreads, DUAL ? 2 : 1) wq_gemm_tc_kernel(co
           fsw[(m4 + 2) * kBN] = sz.x * sc.z * (__uint_as_float(d[m4 + 2]) - zz * sa.z);
           fsw[(m4 + 3) * kBN] = sz.x * sc.w * (__uint_as_float(d[m4 + 3]) - zz * sa.w);
         }
+      } else if (p.norm_sumsq) {  // rows scaled by 1/rms (the activations were bf16(x * gamma))
+        const float* as = ascale + grp * 32;
+#pragma unroll
+        for (int m4 = 0; m4 < 32; m4 += 4) {
+          const float4 sa = *reinterpret_cast<const float4*>(sm + m4);
+          const float4 sc = *reinterpret_cast<const float4*>(as + m4);
+          fsw[(m4 + 0) * kBN] = sz.x * sc.x * (__uint_as_float(d[m4 + 0]) - sz.y * sa.x);
+          fsw[(m4 + 1) * kBN] = sz.x * sc.y * (__uint_as_float(d[m4 + 1]) - sz.y * sa.y);
+          fsw[(m4 + 2) * kBN] = sz.x * sc.z * (__uint_as_float(d[m4 + 2]) - sz.y * sa.z);
+          fsw[(m4 + 3) * kBN] = sz.x * sc.w * (__uint_as_float(d[m4 + 3]) - sz.y * sa.w);
+        }
       } else {
 #pragma unroll
       for (int m4 = 0; m4 < 32; m4 += 4) {
@@ -658,6 +684,7 @@ __global__ void __launch_bounds__(kTcThreads, DUAL ? 2 : 1) wq_gemm_tc_kernel(co
         for (int j = 0; j < UPT; ++j) {
           const int i = tid + j * T;
           const int m = i >> 5, nn = ng * kBN + (i & 31) * 4;
+          float ssq = 0.f;
           if (i < units && nn < p.N) {
             const float4 a = fs4[i];
             float v0 = a.x * p.alpha, v1 = a.y * p.alpha, v2 = a.z * p.alpha, v3 = a.w * p.alpha;
@@ -666,7 +693,20 @@ __global__ void __launch_bounds__(kTcThreads, DUAL ? 2 : 1) wq_gemm_tc_kernel(co
               v0 += bf16_lo(bv.x); v1 += bf16_hi(bv.x); v2 += bf16_lo(bv.y); v3 += bf16_hi(bv.y);
             }
             v0 += bf16_lo(res[j].x); v1 += bf16_hi(res[j].x); v2 += bf16_lo(res[j].y); v3 += bf16_hi(res[j].y);
-            *reinterpret_cast<uint2*>(p.C + (int64_t)m * p.ldc + nn) = make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, v3));
+            const uint2 st2 = make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, v3));
+            *reinterpret_cast<uint2*>(p.C + (int64_t)m * p.ldc + nn) = st2;
+            if (p.xg_out) {  // the next RMSNorm's scaled input and row statistics, from the values as stored (bf16)
+              const float r0 = bf16_lo(st2.x), r1 = bf16_hi(st2.x), r2 = bf16_lo(st2.y), r3 = bf16_hi(st2.y);
+              const uint2 gv = __ldg(reinterpret_cast<const uint2*>(p.gamma_out + nn));
+              *reinterpret_cast<uint2*>(p.xg_out + (int64_t)m * p.ldxg + nn) =
+                  make_uint2(pack_bf16x2(r0 * bf16_lo(gv.x), r1 * bf16_hi(gv.x)), pack_bf16x2(r2 * bf16_lo(gv.y), r3 * bf16_hi(gv.y)));
+              ssq = (r0 * r0 + r1 * r1) + (r2 * r2 + r3 * r3);
+            }
+          }
+          if (p.xg_out) {  // a warp holds the 32 four-column units of one row (416 = 13 x 32): fixed-order lane reduction
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
+            if (lane == 0 && i < units) p.sumsq_out[(size_t)ng * p.norm_ld + m] = ssq;
           }
         }
       } else {
@@ -786,6 +826,8 @@ cudaError_t tc_launch(int wbits, const TcLaunch& a, cudaStream_t stream) {
   p.ws = a.ws; p.counters = a.counters; p.M = a.M; p.N = a.N; p.K = a.K; p.Np = a.Np; p.KT = a.KT; p.NG = a.NG; p.S = a.S;
   p.act = a.act; p.alpha = a.alpha;
   p.a_scale = a.a_scale; p.tile_sums = a.tile_sums;
+  p.norm_sumsq = a.norm_sumsq; p.norm_parts = a.norm_parts; p.norm_ld = a.norm_ld; p.norm_inv_hidden = a.norm_inv_hidden;
+  p.norm_eps = a.norm_eps; p.sumsq_out = a.sumsq_out; p.xg_out = a.xg_out; p.gamma_out = a.gamma_out; p.ldxg = a.ldxg;
   p.nm = nm; p.group_tiles = a.group_tiles;
   p.dbg = 0;
 #ifdef B2_TC_ABLATE

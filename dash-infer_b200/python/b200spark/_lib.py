@@ -34,7 +34,8 @@ class SpanCfg(C.Structure):
 
 class GemmFuse(C.Structure):
     _fields_ = [("norm_sumsq", C.c_void_p), ("norm_gamma", C.c_void_p), ("norm_parts", C.c_int32), ("norm_hidden", C.c_int32),
-                ("norm_eps", C.c_float), ("reserved", C.c_int32), ("sumsq_out", C.c_void_p)]
+                ("norm_eps", C.c_float), ("reserved", C.c_int32), ("sumsq_out", C.c_void_p),
+                ("xg_out", C.c_void_p), ("gamma_out", C.c_void_p), ("ldxg", C.c_int64)]
 
 
 class RopeCfg(C.Structure):

@@ -207,6 +207,14 @@ class DecodeStack:
         # B200 (Qwen2-7B int4, whole step) batch 1: 445 -> 462 tok/s, batch 8: 3241 -> 3140.  Default: batches <= 2.
         self.norm_self = os.environ.get("B2_NORM_SELF", "1") != "0" and not self.fuse_norm
         self.norm_self_max_b = int(os.environ.get("B2_NORM_SELF_MAX_B", "2"))
+        # RMSNorm hand-off between the tcgen05 GEMMs (batches >= 17, TP = 1): o_proj / down_proj also write the next
+        # norm's input scaled by its gamma plus per-tile row statistics; qkv / gate+up / lm_head scale their result rows by
+        # 1/rms.  Only layer 0's first norm stays a stand-alone kernel (2 launches per layer fewer).
+        self.norm_handoff = (os.environ.get("B2_NORM_HANDOFF", "1") != "0" and tp == 1 and not self.fuse_norm
+                             and (group == -1 or wbits == 4))
+        if self.norm_handoff and batch >= 17:
+            self._ssq_o = torch.zeros(self.layers[0]["o"].op.sumsq_parts() * batch, dtype=torch.float32, device=device)
+            self._ssq_d = torch.zeros(self.layers[0]["down"].op.sumsq_parts() * batch, dtype=torch.float32, device=device)
         self.launches_per_step = 0
 
     def set_batch(self, b):
@@ -287,6 +295,10 @@ class DecodeStack:
         H = cfg.hidden
         fn = self.fuse_norm
         ns = self.norm_self and self.B <= min(16, self.norm_self_max_b)
+        nh = self.norm_handoff and self.B >= 17
+        if nh:
+            ssq_o = self._ssq_o[:self._ssq_o.numel() // self.Bmax * self.B].view(-1, self.B)
+            ssq_d = self._ssq_d[:self._ssq_d.numel() // self.Bmax * self.B].view(-1, self.B)
         n = 0
         ops.embedding(self.embed, self.ids, out=self.x); n += 1
         for li, L in enumerate(self.layers):
@@ -294,6 +306,8 @@ class DecodeStack:
                 L["qkv"](self.x, ws, out=self.qkv, norm_in=(self.ssq_d, L["g1"], H, cfg.eps)); n += 1
             elif ns:
                 L["qkv"](self.x, ws, out=self.qkv, norm_in=(None, L["g1"], H, cfg.eps)); n += 1
+            elif nh and li > 0:  # xn = bf16(x * g1) and the row statistics were written by the previous layer's down_proj
+                L["qkv"](self.xn, ws, out=self.qkv, norm_in=(ssq_d, None, H, cfg.eps)); n += 1
             else:
                 ops.rmsnorm(self.x, L["g1"], cfg.eps, out=self.xn); n += 1
                 L["qkv"](self.xn, ws, out=self.qkv); n += 1
@@ -305,6 +319,9 @@ class DecodeStack:
             elif ns:
                 n = self._row_parallel(L["o"], self.ao, n)
                 mlp_in, nin = self.x, (None, L["g2"], H, cfg.eps)
+            elif nh:
+                L["o"](self.ao, ws, out=self.x, residual=self.x, sumsq_out=ssq_o, xg_out=(self.xn, L["g2"])); n += 1
+                mlp_in, nin = self.xn, (ssq_o, None, H, cfg.eps)
             else:
                 n = self._row_parallel(L["o"], self.ao, n)
                 ops.rmsnorm(self.x, L["g2"], cfg.eps, out=self.xn); n += 1
@@ -317,10 +334,15 @@ class DecodeStack:
                 ops.binary(self.gate, self.up, BIN_MUL, out=self.gate); n += 1
             if fn:
                 L["down"](self.gate, ws, out=self.x, residual=self.x, sumsq_out=self.ssq_d); n += 1
+            elif nh:
+                g_next = self.layers[li + 1]["g1"] if li + 1 < len(self.layers) else self.gf
+                L["down"](self.gate, ws, out=self.x, residual=self.x, sumsq_out=ssq_d, xg_out=(self.xn, g_next)); n += 1
             else:
                 n = self._row_parallel(L["down"], self.gate, n)
         if fn:
             self.lm_head(self.x, ws, out=self.logits, norm_in=(self.ssq_d, self.gf, H, cfg.eps)); n += 1
+        elif nh:
+            self.lm_head(self.xn, ws, out=self.logits, norm_in=(ssq_d, None, H, cfg.eps)); n += 1
         else:
             ops.rmsnorm(self.x, self.gf, cfg.eps, out=self.xn); n += 1
             self.lm_head(self.xn, ws, out=self.logits); n += 1

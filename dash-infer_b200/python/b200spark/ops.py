@@ -77,9 +77,10 @@ class GemmWQ:
     def sumsq_parts(self):
         return lib.b2_gemm_wq_sumsq_parts(self.h)
 
-    def __call__(self, a, ws, out=None, act=ACT_NONE, alpha=1.0, residual=None, norm_in=None, sumsq_out=None):
+    def __call__(self, a, ws, out=None, act=ACT_NONE, alpha=1.0, residual=None, norm_in=None, sumsq_out=None, xg_out=None):
         """norm_in = (sumsq [parts, M] fp32 or None, gamma [K] bf16, hidden, eps): fused RMSNorm prologue;
-        sumsq_out [sumsq_parts(), M] fp32: per-tile row sums of squares of the output (for the next op's norm_in)."""
+        sumsq_out [sumsq_parts(), M] fp32: per-tile row sums of squares of the output (for the next op's norm_in).
+        Batches >= 17: norm_in = (sumsq, None, hidden, eps) with `a` = the producer's xg_out (already scaled by gamma)."""
         if self.pair:
             act = _lib.ACT_SWIGLU
         M = a.numel() // a.shape[-1]
@@ -89,17 +90,20 @@ class GemmWQ:
         wsb = ws.reserve(self.workspace_bytes(M))
         lda = a.stride(-2) if a.dim() > 1 else self.K
         ldc = out.stride(-2) if out.dim() > 1 else self.N
-        if norm_in is None and sumsq_out is None:
+        if norm_in is None and sumsq_out is None and xg_out is None:
             check(lib.b2_gemm_wq_run(self.h, _ptr(a), lda, _ptr(out), ldc, M, _ptr(self.bias), _ptr(residual), act,
                                      float(alpha), _ptr(wsb), wsb.numel(), _stream()), "b2_gemm_wq_run")
             return out
         f = GemmFuse()
         if norm_in is not None:
             ss, gamma, hidden, eps = norm_in   # ss None: the GEMV takes the row statistics itself (hidden == K)
-            f.norm_sumsq, f.norm_gamma = (ss.data_ptr() if ss is not None else None), gamma.data_ptr()
+            f.norm_sumsq, f.norm_gamma = (ss.data_ptr() if ss is not None else None), (gamma.data_ptr() if gamma is not None else None)
             f.norm_parts, f.norm_hidden, f.norm_eps = (ss.shape[0] if ss is not None else 0), int(hidden), float(eps)
         if sumsq_out is not None:
             f.sumsq_out = sumsq_out.data_ptr()
+        if xg_out is not None:  # (xg [M, N] bf16, gamma_out [N] bf16): the hand-off form of batches >= 17
+            xg, g_out = xg_out
+            f.xg_out, f.gamma_out, f.ldxg = xg.data_ptr(), g_out.data_ptr(), xg.stride(-2) if xg.dim() > 1 else self.N
         check(lib.b2_gemm_wq_run_fused(self.h, _ptr(a), lda, _ptr(out), ldc, M, _ptr(self.bias), _ptr(residual), act,
                                        float(alpha), _ptr(wsb), wsb.numel(), C.byref(f), _stream()), "b2_gemm_wq_run_fused")
         return out

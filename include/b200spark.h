@@ -129,6 +129,14 @@ typedef struct {
   float norm_eps;
   int32_t reserved;
   float* sumsq_out;        /* [b2_gemm_wq_sumsq_parts(handle)][M] or NULL */
+  /* Batches >= 17 (tcgen05 path): the hand-off form.  The producer (o_proj / down_proj with residual) writes, besides C and
+   * sumsq_out, xg_out[m, n] = FT(C[m, n] * gamma_out[n]) — the next RMSNorm's input already scaled by its gamma; the consumer
+   * is called with A = xg, norm_sumsq = the producer's sumsq_out, norm_gamma = NULL, and multiplies its fp32 result rows by
+   * rsqrt(sum_p norm_sumsq[p][m] / norm_hidden + eps) (the factor is linear in the row).  Two RMSNorm launches per layer
+   * disappear; the statistics are taken from the values as stored (FT), like the stand-alone norm reads them. */
+  void* xg_out;            /* [M, ldxg] FT or NULL (requires sumsq_out and gamma_out) */
+  const void* gamma_out;   /* [N] FT */
+  int64_t ldxg;
 } b2_gemm_fuse;
 int b2_gemm_wq_sumsq_parts(b2_gemm_wq_t handle);
 int b2_gemm_wq_run_fused(b2_gemm_wq_t handle, const void* A, int64_t lda, void* C, int64_t ldc, int M,

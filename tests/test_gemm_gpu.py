@@ -223,6 +223,71 @@ def test_fused_rmsnorm_prologue_and_sumsq_epilogue(wbits, M):
     assert (y_fused != y_ref).float().mean().item() < 0.05
 
 
+@pytest.mark.parametrize("wbits,group,M", [(4, -1, 17), (4, -1, 64), (8, -1, 33), (4, 128, 40), (16, -1, 64), (4, -1, 100)])
+def test_tcgen05_rmsnorm_handoff(wbits, group, M):
+    """Batches >= 17: the producer GEMM (+residual) also writes xg = bf16(C * gamma) and per-tile row statistics; the consumer
+    takes A = xg and scales its result rows by 1/rms.  Producer: C bit-identical to the plain call, xg and the statistics
+    follow the stored bf16 values.  Consumer (plain and gate/up SwiGLU pair): against fp64 RMSNorm -> GEMM math and against
+    the two-kernel path (b2_rmsnorm, then the plain GEMM)."""
+    from b200spark import ops, quantize as PQ
+    H, N2 = 3584, 1280
+    g = torch.Generator().manual_seed(wbits * 10 + M)
+    d = lambda t: t.cuda() if t is not None else None
+
+    def quant(w, K, N):
+        if wbits == 4:
+            q, s, z = PQ.quantize_a16w4(w, group); qu = Q.unpack_u4x2(q.numpy(), N)
+        elif wbits == 8:
+            q, s, z = PQ.quantize_a16w8(w, group); qu = q.numpy()
+        else:
+            return (w, None, None), w.float().numpy().astype(np.float64)
+        gs = K if group == -1 else group
+        sc = np.repeat(s.float().numpy().astype(np.float64), gs, axis=0)[:K]
+        zz = np.repeat(z.float().numpy().astype(np.float64), gs, axis=0)[:K]
+        return (q, s, z), (qu.astype(np.float64) - zz) * sc
+
+    mk = lambda k, n: (torch.randn(k, n, generator=g) * 0.02).to(torch.bfloat16)
+    (qp, sp, zp), _ = quant(mk(H, H), H, H)
+    prod = ops.GemmWQ(H, H, wbits, group, max_m=M).prepare(d(qp), d(sp), d(zp))
+    a = (torch.rand(M, H, generator=g) * 2 - 1).to(torch.bfloat16).cuda()
+    res = (torch.randn(M, H, generator=g) * 2.0).to(torch.bfloat16).cuda()
+    gamma = (1 + 0.2 * torch.randn(H, generator=g)).to(torch.bfloat16).cuda()
+    eps = 1e-6
+    ws = ops.Workspace()
+    ssq = torch.zeros(prod.sumsq_parts(), M, dtype=torch.float32, device="cuda")
+    xg = torch.empty(M, H, dtype=torch.bfloat16, device="cuda")
+    x = prod(a, ws, residual=res, sumsq_out=ssq, xg_out=(xg, gamma))
+    x_plain = prod(a, ws, residual=res)
+    torch.cuda.synchronize()
+    assert torch.equal(x, x_plain)
+    assert torch.equal(xg, (x.float() * gamma.float()).to(torch.bfloat16))
+    assert torch.allclose(ssq.sum(0), x.float().pow(2).sum(-1), rtol=1e-5)
+
+    x64 = x.float().cpu().numpy().astype(np.float64)
+    xn = x64 / np.sqrt((x64 ** 2).mean(-1, keepdims=True) + eps) * gamma.float().cpu().numpy().astype(np.float64)
+    for pair in (False, True):
+        sets, deq = [], []
+        for _ in range(2 if pair else 1):
+            t, wd = quant(mk(H, N2), H, N2)
+            sets.append(t); deq.append(wd)
+        cons = ops.GemmWQ(H, N2, wbits, group, max_m=M, pair=pair)
+        if pair:
+            cons.prepare_swiglu(*[d(t) for t in sets[0]], *[d(t) for t in sets[1]])
+        else:
+            cons.prepare(*[d(t) for t in sets[0]])
+        y = cons(xg, ws, norm_in=(ssq, None, H, eps))
+        y2 = cons(xg, ws, norm_in=(ssq, None, H, eps))
+        y_two = cons(ops.rmsnorm(x, gamma, eps), ws)
+        torch.cuda.synchronize()
+        assert torch.equal(y, y2)
+        outs = [xn @ w for w in deq]
+        ref = ((outs[0] / (1.0 + np.exp(-outs[0]))) * outs[1] if pair else outs[0]).astype(np.float32)
+        e_h = Q.err_min_abs_rel(ref, y.float().cpu().numpy())
+        e_two = Q.err_min_abs_rel(ref, y_two.float().cpu().numpy())
+        assert e_h <= (2 * TOL if pair else TOL), (e_h, e_two)
+        assert e_h <= 2.0 * e_two + 2e-3, (e_h, e_two)
+
+
 @pytest.mark.parametrize("wbits,group,M,N", [(4, -1, 1, 5117), (4, -1, 7, 5120), (8, -1, 16, 5117), (4, 128, 9, 5118), (16, -1, 3, 5117)])
 def test_cluster_split_k_epilogue(monkeypatch, wbits, group, M, N):
     """Shapes wide enough for the thread-block-cluster split-K (the k-slices of a tile meet in distributed shared memory and
