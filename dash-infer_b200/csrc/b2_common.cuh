@@ -226,6 +226,39 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// ---- the 16-bit activation type of a GEMM handle (FT): bf16 (H = false) or fp16 (H = true).  Pointers stay `__nv_bfloat16*`
+// (16-bit storage); everything that interprets the bits goes through this trait.  kMagic / kMagicHi: the "exact integer"
+// dequantisation constants — a 4-bit code OR-ed into mantissa bits 3..6 of {16.0, 256.0} (bf16: 16 + q, 16 (16 + q)) or of
+// {128.0, 2048.0} (fp16, three more mantissa bits: 128 + q, 16 (128 + q)); kBias is the additive constant that comes with it.
+template <bool H>
+struct Ft;
+template <>
+struct Ft<false> {
+  static constexpr uint32_t kMagic = 0x41804180u, kMagicHi = 0x43804380u;
+  static constexpr float kBias = 16.f;
+  static __device__ __forceinline__ float lo(uint32_t v) { return __uint_as_float(v << 16); }
+  static __device__ __forceinline__ float hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+  static __device__ __forceinline__ uint32_t pack(float a, float b) { return pack_bf16x2(a, b); }
+  static __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+  static __device__ __forceinline__ __nv_bfloat16 from_f(float v) { return __float2bfloat16(v); }
+  static __device__ __forceinline__ void mma(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    mma_bf16_16816(d, a0, a1, a2, a3, b0, b1);
+  }
+};
+template <>
+struct Ft<true> {
+  static constexpr uint32_t kMagic = 0x58005800u, kMagicHi = 0x68006800u;
+  static constexpr float kBias = 128.f;
+  static __device__ __forceinline__ float lo(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v & 0xffffu))); }
+  static __device__ __forceinline__ float hi(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v >> 16))); }
+  static __device__ __forceinline__ uint32_t pack(float a, float b) { return pack_f16x2(a, b); }
+  static __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __half2float(__ushort_as_half(__bfloat16_as_ushort(v))); }
+  static __device__ __forceinline__ __nv_bfloat16 from_f(float v) { return __ushort_as_bfloat16(__half_as_ushort(__float2half_rn(v))); }
+  static __device__ __forceinline__ void mma(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    mma_f16_16816(d, a0, a1, a2, a3, b0, b1);
+  }
+};
+
 template <int ACT>
 __device__ __forceinline__ float apply_act(float x) {
   // csrc/core/kernel/cuda/hie/cuda_activation.hpp (reference formulas, fp32)

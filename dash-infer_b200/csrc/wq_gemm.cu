@@ -81,7 +81,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("ba
 
 // One k-tile (64 k x 16 n per warp) of tensor-core work for this warp.  woff0/woff1: byte offsets of this thread's
 // row g / row g+8 data inside the tile; xaddr: this thread's 32 bytes of activations (16 consecutive k).
-template <int WBITS, int MT>
+template <int WBITS, int MT, bool H>
 __device__ __forceinline__ void tile_mma(float (&acc)[MT][4], uint32_t wtile, uint32_t woff0, uint32_t woff1, uint32_t xaddr,
                                          int XS8) {
   uint4 xb[MT][2];
@@ -96,14 +96,14 @@ __device__ __forceinline__ void tile_mma(float (&acc)[MT][4], uint32_t wtile, ui
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const uint32_t u = r0w[j], v = r1w[j];
-      const uint32_t p0 = lop3_and_or(u, kMask4, kMagic), q0 = lop3_and_or(v, kMask4, kMagic);
-      const uint32_t p1 = lop3_and_or(__funnelshift_r(u, u, 4), kMask4, kMagic), q1 = lop3_and_or(__funnelshift_r(v, v, 4), kMask4, kMagic);
-      const uint32_t p2 = lop3_and_or(__funnelshift_r(u, u, 8), kMask4, kMagic), q2 = lop3_and_or(__funnelshift_r(v, v, 8), kMask4, kMagic);
-      const uint32_t p3 = lop3_and_or(__funnelshift_r(u, u, 12), kMask4, kMagic), q3 = lop3_and_or(__funnelshift_r(v, v, 12), kMask4, kMagic);
+      const uint32_t p0 = lop3_and_or(u, kMask4, Ft<H>::kMagic), q0 = lop3_and_or(v, kMask4, Ft<H>::kMagic);
+      const uint32_t p1 = lop3_and_or(__funnelshift_r(u, u, 4), kMask4, Ft<H>::kMagic), q1 = lop3_and_or(__funnelshift_r(v, v, 4), kMask4, Ft<H>::kMagic);
+      const uint32_t p2 = lop3_and_or(__funnelshift_r(u, u, 8), kMask4, Ft<H>::kMagic), q2 = lop3_and_or(__funnelshift_r(v, v, 8), kMask4, Ft<H>::kMagic);
+      const uint32_t p3 = lop3_and_or(__funnelshift_r(u, u, 12), kMask4, Ft<H>::kMagic), q3 = lop3_and_or(__funnelshift_r(v, v, 12), kMask4, Ft<H>::kMagic);
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
-        mma_bf16_16816(acc[m], p0, q0, p1, q1, xb[m][j].x, xb[m][j].y);
-        mma_bf16_16816(acc[m], p2, q2, p3, q3, xb[m][j].z, xb[m][j].w);
+        Ft<H>::mma(acc[m], p0, q0, p1, q1, xb[m][j].x, xb[m][j].y);
+        Ft<H>::mma(acc[m], p2, q2, p3, q3, xb[m][j].z, xb[m][j].w);
       }
     }
   } else if (WBITS == 8) {
@@ -112,16 +112,16 @@ __device__ __forceinline__ void tile_mma(float (&acc)[MT][4], uint32_t wtile, ui
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint32_t u = r0w[j], v = r1w[j];
-      const uint32_t l0 = lop3_and_or(u, kMask4, kMagic), m0 = lop3_and_or(v, kMask4, kMagic);
-      const uint32_t h0 = lop3_and_or(__funnelshift_r(u, u, 4), kMask4, kMagicHi), n0 = lop3_and_or(__funnelshift_r(v, v, 4), kMask4, kMagicHi);
-      const uint32_t l1 = lop3_and_or(__funnelshift_r(u, u, 8), kMask4, kMagic), m1 = lop3_and_or(__funnelshift_r(v, v, 8), kMask4, kMagic);
-      const uint32_t h1 = lop3_and_or(__funnelshift_r(u, u, 12), kMask4, kMagicHi), n1 = lop3_and_or(__funnelshift_r(v, v, 12), kMask4, kMagicHi);
+      const uint32_t l0 = lop3_and_or(u, kMask4, Ft<H>::kMagic), m0 = lop3_and_or(v, kMask4, Ft<H>::kMagic);
+      const uint32_t h0 = lop3_and_or(__funnelshift_r(u, u, 4), kMask4, Ft<H>::kMagicHi), n0 = lop3_and_or(__funnelshift_r(v, v, 4), kMask4, Ft<H>::kMagicHi);
+      const uint32_t l1 = lop3_and_or(__funnelshift_r(u, u, 8), kMask4, Ft<H>::kMagic), m1 = lop3_and_or(__funnelshift_r(v, v, 8), kMask4, Ft<H>::kMagic);
+      const uint32_t h1 = lop3_and_or(__funnelshift_r(u, u, 12), kMask4, Ft<H>::kMagicHi), n1 = lop3_and_or(__funnelshift_r(v, v, 12), kMask4, Ft<H>::kMagicHi);
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
         const uint32_t b0 = (j & 1) ? xb[m][j >> 1].z : xb[m][j >> 1].x;
         const uint32_t b1 = (j & 1) ? xb[m][j >> 1].w : xb[m][j >> 1].y;
-        mma_bf16_16816(acc[m], l0, m0, l1, m1, b0, b1);   // low nibbles:  16 + lo
-        mma_bf16_16816(acc[m], h0, n0, h1, n1, b0, b1);   // high nibbles: 16 * (16 + hi)
+        Ft<H>::mma(acc[m], l0, m0, l1, m1, b0, b1);   // low nibbles:  16 + lo
+        Ft<H>::mma(acc[m], h0, n0, h1, n1, b0, b1);   // high nibbles: 16 * (16 + hi)
       }
     }
   } else {
@@ -130,8 +130,8 @@ __device__ __forceinline__ void tile_mma(float (&acc)[MT][4], uint32_t wtile, ui
       const uint4 w0 = lds128(wtile + woff0 + u * 2048), w1 = lds128(wtile + woff1 + u * 2048);
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
-        mma_bf16_16816(acc[m], w0.x, w1.x, w0.y, w1.y, xb[m][u].x, xb[m][u].y);
-        mma_bf16_16816(acc[m], w0.z, w1.z, w0.w, w1.w, xb[m][u].z, xb[m][u].w);
+        Ft<H>::mma(acc[m], w0.x, w1.x, w0.y, w1.y, xb[m][u].x, xb[m][u].y);
+        Ft<H>::mma(acc[m], w0.z, w1.z, w0.w, w1.w, xb[m][u].z, xb[m][u].w);
       }
     }
   }
@@ -142,9 +142,10 @@ B2_TRACE_DECL(g_gemv_tr)
 extern "C" int b2_debug_trace_gemv(unsigned long long* host_out) { return (int)cudaMemcpyFromSymbol(host_out, g_gemv_tr, sizeof(g_gemv_tr)); }
 #endif
 
-template <int WBITS, int MT, bool GROUPED>
+template <int WBITS, int MT, bool GROUPED, bool H>
 __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
   using T = WTraits<WBITS>;
+  using F = Ft<H>;  // bf16 / fp16 activations, outputs, bias, residual
   constexpr int MP = 8 * MT;
   const int NST = 1 << p.nst_log2;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -282,15 +283,15 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
               if (p.norm_sumsq) {  // same fp32 op order and rounding as rmsnorm_kernel: (x * inv) * gamma -> bf16
                 const uint4 gv = *reinterpret_cast<const uint4*>(p.norm_gamma + kbase + v * 8);
                 const float inv = sinv[m];
-                val.x = pack_bf16x2(bf16_lo(val.x) * inv * bf16_lo(gv.x), bf16_hi(val.x) * inv * bf16_hi(gv.x));
-                val.y = pack_bf16x2(bf16_lo(val.y) * inv * bf16_lo(gv.y), bf16_hi(val.y) * inv * bf16_hi(gv.y));
-                val.z = pack_bf16x2(bf16_lo(val.z) * inv * bf16_lo(gv.z), bf16_hi(val.z) * inv * bf16_hi(gv.z));
-                val.w = pack_bf16x2(bf16_lo(val.w) * inv * bf16_lo(gv.w), bf16_hi(val.w) * inv * bf16_hi(gv.w));
+                val.x = F::pack(F::lo(val.x) * inv * F::lo(gv.x), F::hi(val.x) * inv * F::hi(gv.x));
+                val.y = F::pack(F::lo(val.y) * inv * F::lo(gv.y), F::hi(val.y) * inv * F::hi(gv.y));
+                val.z = F::pack(F::lo(val.z) * inv * F::lo(gv.z), F::hi(val.z) * inv * F::hi(gv.z));
+                val.w = F::pack(F::lo(val.w) * inv * F::lo(gv.w), F::hi(val.w) * inv * F::hi(gv.w));
               }
             }
             *reinterpret_cast<uint4*>(xrow + v * 16) = val;
-            sacc += (bf16_lo(val.x) + bf16_hi(val.x)) + (bf16_lo(val.y) + bf16_hi(val.y)) +
-                    (bf16_lo(val.z) + bf16_hi(val.z)) + (bf16_lo(val.w) + bf16_hi(val.w));
+            sacc += (F::lo(val.x) + F::hi(val.x)) + (F::lo(val.y) + F::hi(val.y)) +
+                    (F::lo(val.z) + F::hi(val.z)) + (F::lo(val.w) + F::hi(val.w));
           }
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
@@ -339,28 +340,28 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
                   // self-contained RMSNorm: bf16(x * gamma) feeds the MMAs, sum x^2 of this CTA's k-slice is collected on
                   // the way; the 1/rms factor is linear in the row and is applied to the reduced fp32 tile in the epilogue
                   const uint4 gv = *reinterpret_cast<const uint4*>(grow + v * 16);
-                  const float x0 = bf16_lo(val.x), x1 = bf16_hi(val.x), x2 = bf16_lo(val.y), x3 = bf16_hi(val.y);
-                  const float x4 = bf16_lo(val.z), x5 = bf16_hi(val.z), x6 = bf16_lo(val.w), x7 = bf16_hi(val.w);
+                  const float x0 = F::lo(val.x), x1 = F::hi(val.x), x2 = F::lo(val.y), x3 = F::hi(val.y);
+                  const float x4 = F::lo(val.z), x5 = F::hi(val.z), x6 = F::lo(val.w), x7 = F::hi(val.w);
                   ssq += (x0 * x0 + x1 * x1) + (x2 * x2 + x3 * x3) + (x4 * x4 + x5 * x5) + (x6 * x6 + x7 * x7);
-                  val.x = pack_bf16x2(x0 * bf16_lo(gv.x), x1 * bf16_hi(gv.x));
-                  val.y = pack_bf16x2(x2 * bf16_lo(gv.y), x3 * bf16_hi(gv.y));
-                  val.z = pack_bf16x2(x4 * bf16_lo(gv.z), x5 * bf16_hi(gv.z));
-                  val.w = pack_bf16x2(x6 * bf16_lo(gv.w), x7 * bf16_hi(gv.w));
+                  val.x = F::pack(x0 * F::lo(gv.x), x1 * F::hi(gv.x));
+                  val.y = F::pack(x2 * F::lo(gv.y), x3 * F::hi(gv.y));
+                  val.z = F::pack(x4 * F::lo(gv.z), x5 * F::hi(gv.z));
+                  val.w = F::pack(x6 * F::lo(gv.w), x7 * F::hi(gv.w));
                   *reinterpret_cast<uint4*>(xrow + v * 16) = val;
                 } else if (p.norm_sumsq) {  // same fp32 op order and rounding as rmsnorm_kernel: (x * inv) * gamma -> bf16
                   const uint4 gv = *reinterpret_cast<const uint4*>(p.norm_gamma + kbase + v * 8);
                   const float inv = sinv[m];
-                  val.x = pack_bf16x2(bf16_lo(val.x) * inv * bf16_lo(gv.x), bf16_hi(val.x) * inv * bf16_hi(gv.x));
-                  val.y = pack_bf16x2(bf16_lo(val.y) * inv * bf16_lo(gv.y), bf16_hi(val.y) * inv * bf16_hi(gv.y));
-                  val.z = pack_bf16x2(bf16_lo(val.z) * inv * bf16_lo(gv.z), bf16_hi(val.z) * inv * bf16_hi(gv.z));
-                  val.w = pack_bf16x2(bf16_lo(val.w) * inv * bf16_lo(gv.w), bf16_hi(val.w) * inv * bf16_hi(gv.w));
+                  val.x = F::pack(F::lo(val.x) * inv * F::lo(gv.x), F::hi(val.x) * inv * F::hi(gv.x));
+                  val.y = F::pack(F::lo(val.y) * inv * F::lo(gv.y), F::hi(val.y) * inv * F::hi(gv.y));
+                  val.z = F::pack(F::lo(val.z) * inv * F::lo(gv.z), F::hi(val.z) * inv * F::hi(gv.z));
+                  val.w = F::pack(F::lo(val.w) * inv * F::lo(gv.w), F::hi(val.w) * inv * F::hi(gv.w));
                   *reinterpret_cast<uint4*>(xrow + v * 16) = val;
                 }
               } else {
                 *reinterpret_cast<uint4*>(xrow + v * 16) = val;  // k >= K
               }
-              sacc += (bf16_lo(val.x) + bf16_hi(val.x)) + (bf16_lo(val.y) + bf16_hi(val.y)) +
-                      (bf16_lo(val.z) + bf16_hi(val.z)) + (bf16_lo(val.w) + bf16_hi(val.w));
+              sacc += (F::lo(val.x) + F::hi(val.x)) + (F::lo(val.y) + F::hi(val.y)) +
+                      (F::lo(val.z) + F::hi(val.z)) + (F::lo(val.w) + F::hi(val.w));
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
@@ -396,7 +397,7 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
           sz0 = p.sz[(size_t)grp * p.Np + n0];
           sz1 = p.sz[(size_t)grp * p.Np + n0 + 8];
         }
-        tile_mma<WBITS, MT>(acc, wst + ti * T::TILE_BYTES, woff0, woff1, x_thr + (xs0 + ti) * 128, XS8);
+        tile_mma<WBITS, MT, H>(acc, wst + ti * T::TILE_BYTES, woff0, woff1, x_thr + (xs0 + ti) * 128, XS8);
         if (GROUPED && ++gcount == gt) {  // fold this quant group into the fp32 result
           gcount = 0;
           const int gi = (xs0 + ti) / gt;
@@ -481,11 +482,11 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
                               apply_act<B2_ACT_SILU>(gq.z * ra) * (uq.z * ra), apply_act<B2_ACT_SILU>(gq.w * ra) * (uq.w * ra)};
           __nv_bfloat16* cp = p.C + (int64_t)m * p.ldc + n;
           if (n + 3 < p.N && (reinterpret_cast<uintptr_t>(cp) & 7) == 0) {
-            *reinterpret_cast<uint2*>(cp) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+            *reinterpret_cast<uint2*>(cp) = make_uint2(F::pack(v[0], v[1]), F::pack(v[2], v[3]));
           } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              if (n + j < p.N) cp[j] = __float2bfloat16(v[j]);
+              if (n + j < p.N) cp[j] = F::from_f(v[j]);
           }
         }
       } else {
@@ -501,17 +502,17 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             if (n + j < p.N) {
-              if (p.bias) v[j] += __bfloat162float(p.bias[n + j]);
+              if (p.bias) v[j] += F::to_f(p.bias[n + j]);
               v[j] = apply_act_rt(v[j], p.act);
-              if (rp) v[j] += __bfloat162float(rp[j]);
+              if (rp) v[j] += F::to_f(rp[j]);
             }
           }
           if (n + 3 < p.N && (reinterpret_cast<uintptr_t>(cp) & 7) == 0) {
-            *reinterpret_cast<uint2*>(cp) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+            *reinterpret_cast<uint2*>(cp) = make_uint2(F::pack(v[0], v[1]), F::pack(v[2], v[3]));
           } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              if (n + j < p.N) cp[j] = __float2bfloat16(v[j]);
+              if (n + j < p.N) cp[j] = F::from_f(v[j]);
           }
         }
       }
@@ -602,10 +603,10 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
       const float u0 = fs[m * kBN + 64 + np * 2] * ra, u1 = fs[m * kBN + 64 + np * 2 + 1] * ra;
       const float v0 = apply_act<B2_ACT_SILU>(g0) * u0, v1 = apply_act<B2_ACT_SILU>(g1) * u1;
       __nv_bfloat16* cp = p.C + (int64_t)m * p.ldc + n;
-      if ((n + 1) < p.N && ((reinterpret_cast<uintptr_t>(cp) & 3) == 0)) *reinterpret_cast<uint32_t*>(cp) = pack_bf16x2(v0, v1);
+      if ((n + 1) < p.N && ((reinterpret_cast<uintptr_t>(cp) & 3) == 0)) *reinterpret_cast<uint32_t*>(cp) = F::pack(v0, v1);
       else {
-        cp[0] = __float2bfloat16(v0);
-        if ((n + 1) < p.N) cp[1] = __float2bfloat16(v1);
+        cp[0] = F::from_f(v0);
+        if ((n + 1) < p.N) cp[1] = F::from_f(v1);
       }
     }
     return;
@@ -627,10 +628,10 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
       if (n >= p.N) continue;
       float v0 = fs[m * kBN + np * 2] * p.alpha, v1 = fs[m * kBN + np * 2 + 1] * p.alpha;
       if (p.bias) {
-        v0 += __bfloat162float(p.bias[n]);
-        v1 += __bfloat162float(p.bias[n + 1]);
+        v0 += F::to_f(p.bias[n]);
+        v1 += F::to_f(p.bias[n + 1]);
       }
-      const uint32_t pk = pack_bf16x2(v0, v1);
+      const uint32_t pk = F::pack(v0, v1);
       const size_t off = my_slot + ((size_t)m * p.N + n) * 2;
       for (int r = 0; r < cd.nranks; ++r) *reinterpret_cast<uint32_t*>(cd.peer[(cd.rank + r) % cd.nranks] + off) = pk;
     }
@@ -658,15 +659,15 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
         float a0 = 0.f, a1 = 0.f;
         for (int r = 0; r < cd.nranks; ++r) {
           const uint32_t v = __ldcg(reinterpret_cast<const uint32_t*>(base + comm_slot_offset(cd, par, r) + eo));
-          a0 += bf16_lo(v);
-          a1 += bf16_hi(v);
+          a0 += F::lo(v);
+          a1 += F::hi(v);
         }
         if (p.residual) {
           const uint32_t v = *reinterpret_cast<const uint32_t*>(p.residual + (int64_t)m * p.ldc + n);
-          a0 += bf16_lo(v);
-          a1 += bf16_hi(v);
+          a0 += F::lo(v);
+          a1 += F::hi(v);
         }
-        *reinterpret_cast<uint32_t*>(p.C + (int64_t)m * p.ldc + n) = pack_bf16x2(a0, a1);
+        *reinterpret_cast<uint32_t*>(p.C + (int64_t)m * p.ldc + n) = F::pack(a0, a1);
       }
     }
     named_bar_sync(1, kWarps * 32);
@@ -688,26 +689,26 @@ __global__ void __launch_bounds__(kThreads) wq_gemm_kernel(const GemmParams p) {
     float v0 = fs[m * kBN + np * 2] * ra, v1 = fs[m * kBN + np * 2 + 1] * ra;
     const bool has1 = (n + 1) < p.N;
     if (p.bias) {
-      v0 += __bfloat162float(p.bias[n]);
-      if (has1) v1 += __bfloat162float(p.bias[n + 1]);
+      v0 += F::to_f(p.bias[n]);
+      if (has1) v1 += F::to_f(p.bias[n + 1]);
     }
     v0 = apply_act_rt(v0, p.act);
     v1 = apply_act_rt(v1, p.act);
     __nv_bfloat16* cp = p.C + (int64_t)m * p.ldc + n;
     if (p.residual) {
       const __nv_bfloat16* rp = p.residual + (int64_t)m * p.ldc + n;
-      v0 += __bfloat162float(rp[0]);
-      if (has1) v1 += __bfloat162float(rp[1]);
+      v0 += F::to_f(rp[0]);
+      if (has1) v1 += F::to_f(rp[1]);
     }
     if (has1 && ((reinterpret_cast<uintptr_t>(cp) & 3) == 0)) {
-      *reinterpret_cast<uint32_t*>(cp) = pack_bf16x2(v0, v1);
+      *reinterpret_cast<uint32_t*>(cp) = F::pack(v0, v1);
     } else {
-      cp[0] = __float2bfloat16(v0);
-      if (has1) cp[1] = __float2bfloat16(v1);
+      cp[0] = F::from_f(v0);
+      if (has1) cp[1] = F::from_f(v1);
     }
     if (p.sumsq_out) {  // keep what was actually stored (bf16-rounded) for the row statistics below
-      fs[m * kBN + np * 2] = __bfloat162float(__float2bfloat16(v0));
-      fs[m * kBN + np * 2 + 1] = has1 ? __bfloat162float(__float2bfloat16(v1)) : 0.f;
+      fs[m * kBN + np * 2] = F::to_f(F::from_f(v0));
+      fs[m * kBN + np * 2 + 1] = has1 ? F::to_f(F::from_f(v1)) : 0.f;
     }
   }
   if (ng == 0 && ctid == 0) B2_TR(g_gemv_tr, 11);
@@ -810,7 +811,7 @@ __global__ void pack_w16_kernel(uint32_t* __restrict__ dst, const uint16_t* __re
 // (scale, zero) bf16 [G][N] -> float2 [G][Np] with the integer-bias constant folded into the zero
 __global__ void pack_sz_kernel(float2* __restrict__ dst, const __nv_bfloat16* __restrict__ scales,
                                const __nv_bfloat16* __restrict__ zeros, const __nv_bfloat16* __restrict__ scales2,
-                               const __nv_bfloat16* __restrict__ zeros2, int pair, int G, int N, int Np, float zbias) {
+                               const __nv_bfloat16* __restrict__ zeros2, int pair, int G, int N, int Np, float zbias, int fp16) {
   const int64_t total = (int64_t)G * Np;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int np = i % Np, gi = i / Np;
@@ -819,7 +820,10 @@ __global__ void pack_sz_kernel(float2* __restrict__ dst, const __nv_bfloat16* __
     const __nv_bfloat16* sc = (pair && r >= 64) ? scales2 : scales;
     const __nv_bfloat16* zr = (pair && r >= 64) ? zeros2 : zeros;
     float2 v = make_float2(0.f, 0.f);
-    if (n < N) v = make_float2(__bfloat162float(sc[(int64_t)gi * N + n]), __bfloat162float(zr[(int64_t)gi * N + n]) + zbias);
+    if (n < N) {
+      const __nv_bfloat16 sv = sc[(int64_t)gi * N + n], zv = zr[(int64_t)gi * N + n];
+      v = fp16 ? make_float2(Ft<true>::to_f(sv), Ft<true>::to_f(zv) + zbias) : make_float2(Ft<false>::to_f(sv), Ft<false>::to_f(zv) + zbias);
+    }
     dst[i] = v;
   }
 }
@@ -855,18 +859,22 @@ struct b2_gemm_wq {
 
 typedef void (*gemm_kernel_t)(const GemmParams);
 
-template <int WBITS, bool GROUPED>
+template <int WBITS, bool GROUPED, bool H>
 static gemm_kernel_t pick_mt(int mt) {
   switch (mt) {
-    case 1: return wq_gemm_kernel<WBITS, 1, GROUPED>;
-    case 2: return wq_gemm_kernel<WBITS, 2, GROUPED>;
-    default: return wq_gemm_kernel<WBITS, 4, GROUPED>;
+    case 1: return wq_gemm_kernel<WBITS, 1, GROUPED, H>;
+    case 2: return wq_gemm_kernel<WBITS, 2, GROUPED, H>;
+    default: return wq_gemm_kernel<WBITS, 4, GROUPED, H>;
   }
 }
-static gemm_kernel_t pick_kernel(int wbits, bool grouped, int mt) {
-  if (wbits == 4) return grouped ? pick_mt<4, true>(mt) : pick_mt<4, false>(mt);
-  if (wbits == 8) return grouped ? pick_mt<8, true>(mt) : pick_mt<8, false>(mt);
-  return pick_mt<16, false>(mt);
+template <bool H>
+static gemm_kernel_t pick_kernel_ft(int wbits, bool grouped, int mt) {
+  if (wbits == 4) return grouped ? pick_mt<4, true, H>(mt) : pick_mt<4, false, H>(mt);
+  if (wbits == 8) return grouped ? pick_mt<8, true, H>(mt) : pick_mt<8, false, H>(mt);
+  return pick_mt<16, false, H>(mt);
+}
+static gemm_kernel_t pick_kernel(int wbits, bool grouped, int mt, bool fp16) {
+  return fp16 ? pick_kernel_ft<true>(wbits, grouped, mt) : pick_kernel_ft<false>(wbits, grouped, mt);
 }
 static int stage_bytes_of(int wbits) { return wbits == 16 ? WTraits<16>::STAGE_BYTES : kStageBytes; }
 static int tile_bytes_of(int wbits) { return wbits == 4 ? WTraits<4>::TILE_BYTES : (wbits == 8 ? WTraits<8>::TILE_BYTES : WTraits<16>::TILE_BYTES); }
@@ -898,7 +906,7 @@ static int make_plan(b2_gemm_wq* h, int mti) {
   const int gt = grouped ? h->group_tiles : 1;
   const int quanta = h->KT / gt;
   const int sms = sm_count();
-  gemm_kernel_t kern = pick_kernel(h->d.wbits, grouped, mt);
+  gemm_kernel_t kern = pick_kernel(h->d.wbits, grouped, mt, h->d.ft == B2_DT_F16);
   const int ring_kb = env_int("B2_GEMM_RING_KB", 32);
   auto log2_stages = [&](int kb) {
     int l = 1;
@@ -991,7 +999,7 @@ int b2_gemm_wq_create(b2_gemm_wq_t* out, const b2_gemm_wq_desc* d) {
   if (!out || !d) return B2_ERR_PARAM;
   if (d->K <= 0 || d->N <= 0 || d->max_m <= 0) return B2_ERR_PARAM;
   if (d->wbits != 4 && d->wbits != 8 && d->wbits != 16) return B2_ERR_PARAM;
-  if (d->ft != B2_DT_BF16) return B2_ERR_UNSUPPORTED;
+  if (d->ft != B2_DT_BF16 && d->ft != B2_DT_F16) return B2_ERR_UNSUPPORTED;
   if (d->wbits == 4 && d->qtype != B2_DT_U8) return B2_ERR_PARAM;  // gemm_a16w4.cpp:104-110: uint8(uint4x2) only
   if (d->wbits == 8 && d->qtype != B2_DT_U8 && d->qtype != B2_DT_I8) return B2_ERR_PARAM;
   if (d->K % 8 != 0) return B2_ERR_UNSUPPORTED;
@@ -1070,11 +1078,13 @@ static int prepare_impl(b2_gemm_wq_t h, const void* qdata, const void* scales, c
       h->own_sz = true;
     }
     // 16+q trick: W4 raw = sum a*(16+q); W8 raw = 16*sum a*(16+hi) + sum a*(16+lo) = sum a*(272+u), u = q (+128 if int8)
-    const float zbias = d.wbits == 4 ? 16.f : (d.qtype == B2_DT_I8 ? 272.f + 128.f : 272.f);
+    // (fp16 handles: 128 + q, so 128 and 17 * 128 = 2176)
+    const float b0 = d.ft == B2_DT_F16 ? 128.f : 16.f;
+    const float zbias = d.wbits == 4 ? b0 : (d.qtype == B2_DT_I8 ? 17.f * b0 + 128.f : 17.f * b0);
     const int64_t tot = (int64_t)h->G * h->Np;
     pack_sz_kernel<<<(int)((tot + 255) / 256), 256, 0, stream>>>(h->sz, (const __nv_bfloat16*)scales, (const __nv_bfloat16*)zeros,
                                                                  (const __nv_bfloat16*)scales2, (const __nv_bfloat16*)zeros2, pair,
-                                                                 h->G, d.N, h->Np, zbias);
+                                                                 h->G, d.N, h->Np, zbias, d.ft == B2_DT_F16 ? 1 : 0);
     if (int st = launch_failed("pack_sz")) return st;
   }
   return B2_OK;
@@ -1195,7 +1205,7 @@ int b2_gemm_wq_run_fp8(b2_gemm_wq_t h, const void* A8, int64_t lda_bytes, const 
   if (!h || !A8 || !a_scale || !tile_sums || !C || M <= 0) return B2_ERR_PARAM;
   if (!h->packed) return B2_ERR_RUNTIME;
   if (M > h->d.max_m) return B2_ERR_LIMIT;
-  if (h->d.wbits != 4 || h->group_tiles > 0) return B2_ERR_UNSUPPORTED;  // int4 per-channel weights (the IQ default)
+  if (h->d.wbits != 4 || h->group_tiles > 0 || h->d.ft != B2_DT_BF16) return B2_ERR_UNSUPPORTED;  // int4 per-channel weights (the IQ default), bf16 outputs
   if (h->pair != (activation == B2_ACT_SWIGLU)) return B2_ERR_PARAM;
   if (activation != B2_ACT_SWIGLU && (activation < 0 || activation > B2_ACT_SIGMOID)) return B2_ERR_PARAM;
   if (h->pair && (bias || residual)) return B2_ERR_UNSUPPORTED;
@@ -1280,6 +1290,7 @@ static int run_impl(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, int64_t
     for (int m0 = 0; m0 < M; m0 += kTcMaxM) {
       TcLaunch a;
       a.dual = dual;
+      a.fp16 = h->d.ft == B2_DT_F16;
       a.packed = (const uint8_t*)h->packed; a.sz = h->sz;
       a.A = (const __nv_bfloat16*)A + (int64_t)m0 * lda; a.lda = lda;
       a.C = (__nv_bfloat16*)C + (int64_t)m0 * ldc; a.ldc = ldc;
@@ -1311,7 +1322,7 @@ static int run_impl(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, int64_t
     return B2_OK;
   }
   // ---- batches <= 32 without global split-K (wq_gemv2.cu) unless a fusion only the split-K kernel implements is asked for
-  if (!fused && !comm) {
+  if (!fused && !comm && h->d.ft == B2_DT_BF16) {  // (fp16 handles: the split-K kernel)
     for (int m0 = 0; m0 < M; m0 += 32) {
       Gemv2Launch a;
       a.packed = (const uint8_t*)h->packed; a.sz = h->sz;
@@ -1372,7 +1383,7 @@ splitk:
     p.comm_on = comm ? 1 : 0;
     if (comm) p.comm = *comm;
     else memset(&p.comm, 0, sizeof(p.comm));
-    gemm_kernel_t kern = pick_kernel(h->d.wbits, grouped, 1 << mti);
+    gemm_kernel_t kern = pick_kernel(h->d.wbits, grouped, 1 << mti, h->d.ft == B2_DT_F16);
     cudaError_t e = pl.cluster ? launch_cluster(kern, dim3(h->NG * pl.S), dim3(kThreads), (size_t)pl.smem, stream, true, (unsigned)pl.S, p)
                                : launch(kern, dim3(h->NG * pl.S), dim3(kThreads), (size_t)pl.smem, stream, true, p);
     if (e != cudaSuccess) {

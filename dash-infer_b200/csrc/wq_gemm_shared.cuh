@@ -38,6 +38,7 @@ struct TcLaunch {
   const float* a_scale = nullptr;    // != NULL: A is fp8-e4m3 in the b2 fp8 activation layout (lda in bytes)
   const float* tile_sums = nullptr;  // [M][KT] sums of the quantized activations per 64-k tile
   int group_tiles = 0;               // > 0: sub-channel weights, k-tiles per quantization group (sz is [G][Np])
+  bool fp16 = false;                 // activations / outputs / bias / residual are fp16 (else bf16)
   bool dual = false;                 // two CTAs per SM (int4 weights, bf16 activations): half-depth stages, 256 TMEM columns
   // RMSNorm hand-off between GEMMs (b2_gemm_fuse, batches >= 17).  Consumer: A holds bf16(x * gamma); the result rows are
   // scaled by rsqrt(sum_p norm_sumsq[p * norm_ld + m] / hidden + eps).  Producer: besides C it writes xg = bf16(C * gamma_out)

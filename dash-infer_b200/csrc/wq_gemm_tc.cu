@@ -178,7 +178,8 @@ struct TcParams {
 // TMEM columns of dequantized A), so a CTA needs 97 KB of shared memory and 256 TMEM columns; the fixed part of a unit —
 // prologue, pipeline fill, accumulator read-out, split-K hand-off, epilogue (6.4 of 17.6 us on the gate projection,
 // profiles/r2_timelines.md) — overlaps the main loop of the CTA next to it instead of idling the SM.
-template <int WBITS, bool MULTI, bool A8 = false, bool GROUPED = false, bool DUAL = false>
+// H: fp16 activations / outputs (kind::f16 takes either 16-bit format; the exact-integer constants are 128 + q instead of 16 + q).
+template <int WBITS, bool MULTI, bool A8 = false, bool GROUPED = false, bool DUAL = false, bool H = false>
 __global__ void __launch_bounds__(kTcThreads, DUAL ? 2 : 1) wq_gemm_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap amap) {
   constexpr int TILE_BYTES = WBITS == 4 ? 4096 : (WBITS == 8 ? 8192 : 16384);
   constexpr int NCH = WBITS == 4 ? 2 : (WBITS == 8 ? 4 : 8);  // 16B chunks per row per k-tile
@@ -188,7 +189,9 @@ __global__ void __launch_bounds__(kTcThreads, DUAL ? 2 : 1) wq_gemm_tc_kernel(co
   constexpr int TPS = WBITS == 4 ? (DUAL ? 2 : 4) : 2;
   constexpr int TMEM_COLS = DUAL ? 256 : kTcTmemCols;
   static_assert(!A8 || WBITS == 4, "fp8 activations: int4 weights only");
-  static_assert(!DUAL || (WBITS == 4 && !A8), "two CTAs per SM: int4 weights, bf16 activations");
+  static_assert(!DUAL || (WBITS == 4 && !A8), "two CTAs per SM: int4 weights, 16-bit activations");
+  static_assert(!H || !A8, "fp8 activations come with bf16 outputs");
+  using F = Ft<H>;
   static_assert(!GROUPED || (!A8 && WBITS != 16), "sub-channel weights: bf16 activations, int4 / int8");
   const int XTILE_LD = p.nm * 128;             // bytes the TMA writes per activation tile (the tile slot stays 64 rows)
   constexpr int ACOLS = A8 ? 16 : (WBITS == 8 ? 64 : 32);  // TMEM columns of dequantized A per k-tile (int8: lo and hi planes)
@@ -320,7 +323,7 @@ __global__ void __launch_bounds__(kTcThreads, DUAL ? 2 : 1) wq_gemm_tc_kernel(co
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N = NM, M = 128 (cute::UMMA::InstrDescriptor)
       // (fp8: a_format = b_format = 0 = E4M3)
       const uint32_t idesc = A8 ? ((1u << 4) | ((nm_u >> 3) << 17) | ((uint32_t)(128 >> 4) << 24))
-                                : ((1u << 4) | (1u << 7) | (1u << 10) | ((nm_u >> 3) << 17) | ((uint32_t)(128 >> 4) << 24));
+                                : ((1u << 4) | (H ? 0u : ((1u << 7) | (1u << 10))) | ((nm_u >> 3) << 17) | ((uint32_t)(128 >> 4) << 24));
       // B smem descriptor (cute::UMMA::SmemDescriptor): K-major, SWIZZLE_128B, SBO = 1024 B (8-row groups), version 1
       const uint64_t desc_hi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
       const uint32_t xbase = smem_u32(xring);
@@ -405,10 +408,10 @@ __global__ void __launch_bounds__(kTcThreads, DUAL ? 2 : 1) wq_gemm_tc_kernel(co
         for (int c = 0; c < 8; c += 2) {
           const uint4 v = lds128(rbase + ((c ^ (xt & 7)) << 4));
           const uint4 w = lds128(rbase + (((c + 1) ^ (xt & 7)) << 4));
-          r0 += (bf16_lo(v.x) + bf16_hi(v.x)) + (bf16_lo(v.y) + bf16_hi(v.y));
-          r1 += (bf16_lo(v.z) + bf16_hi(v.z)) + (bf16_lo(v.w) + bf16_hi(v.w));
-          r2 += (bf16_lo(w.x) + bf16_hi(w.x)) + (bf16_lo(w.y) + bf16_hi(w.y));
-          r3 += (bf16_lo(w.z) + bf16_hi(w.z)) + (bf16_lo(w.w) + bf16_hi(w.w));
+          r0 += (F::lo(v.x) + F::hi(v.x)) + (F::lo(v.y) + F::hi(v.y));
+          r1 += (F::lo(v.z) + F::hi(v.z)) + (F::lo(v.w) + F::hi(v.w));
+          r2 += (F::lo(w.x) + F::hi(w.x)) + (F::lo(w.y) + F::hi(w.y));
+          r3 += (F::lo(w.z) + F::hi(w.z)) + (F::lo(w.w) + F::hi(w.w));
         }
       }
       __syncwarp();
@@ -441,9 +444,9 @@ __global__ void __launch_bounds__(kTcThreads, DUAL ? 2 : 1) wq_gemm_tc_kernel(co
         for (int ti = 0; ti < TPS; ++ti) {
           const int kt = min(kt0 + st * TPS + ti, kt1 - 1);
           const float2 z = __ldg(p.sz + (size_t)(kt / p.group_tiles) * p.Np + ng * kBN + r);  // (scale, zero + 16)
-          gs2[ti] = pack_bf16x2(z.x, z.x);
-          const float c = (24.f - z.y) * z.x;                                                  // (8 - zero) * scale
-          gc2[ti] = pack_bf16x2(c, c);
+          gs2[ti] = F::pack(z.x, z.x);
+          const float c = (F::kBias + 8.f - z.y) * z.x;                                        // (8 - zero) * scale
+          gc2[ti] = F::pack(c, c);
         }
       }
       mbar_wait(&wfull[slot], (g / NSW) & 1);
@@ -482,17 +485,22 @@ __global__ void __launch_bounds__(kTcThreads, DUAL ? 2 : 1) wq_gemm_tc_kernel(co
 #pragma unroll
                 for (int jw = 0; jw < 2; ++jw) {
                   const uint32_t w = ww[2 * h + jw];
-                  a[4 * jw + 0] = lop3_and_or(w, kMask4, kMagic);
-                  a[4 * jw + 1] = lop3_and_or(__funnelshift_r(w, w, 4), kMask4, kMagic);
-                  a[4 * jw + 2] = lop3_and_or(__funnelshift_r(w, w, 8), kMask4, kMagic);
-                  a[4 * jw + 3] = lop3_and_or(__funnelshift_r(w, w, 12), kMask4, kMagic);
+                  a[4 * jw + 0] = lop3_and_or(w, kMask4, F::kMagic);
+                  a[4 * jw + 1] = lop3_and_or(__funnelshift_r(w, w, 4), kMask4, F::kMagic);
+                  a[4 * jw + 2] = lop3_and_or(__funnelshift_r(w, w, 8), kMask4, F::kMagic);
+                  a[4 * jw + 3] = lop3_and_or(__funnelshift_r(w, w, 12), kMask4, F::kMagic);
                 }
                 if (GROUPED) {  // (16 + q) - 24 = q - 8 exactly, then one fused multiply-add: (q - 8) s + (8 - z) s
 #pragma unroll
                   for (int e = 0; e < 8; ++e) {
                     uint32_t t2;
-                    asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(t2) : "r"(a[e]), "r"(0xC1C0C1C0u));
-                    asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(a[e]) : "r"(t2), "r"(gs2[ti]), "r"(gc2[ti]));
+                    if (H) {  // (128 + q) - 136
+                      asm("add.rn.f16x2 %0, %1, %2;" : "=r"(t2) : "r"(a[e]), "r"(0xD840D840u));
+                      asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(a[e]) : "r"(t2), "r"(gs2[ti]), "r"(gc2[ti]));
+                    } else {
+                      asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(t2) : "r"(a[e]), "r"(0xC1C0C1C0u));
+                      asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(a[e]) : "r"(t2), "r"(gs2[ti]), "r"(gc2[ti]));
+                    }
                   }
                 }
                 if (!TC_ABL(16)) tc_st8(acol + (2 * c + h) * 8, a);
@@ -515,10 +523,10 @@ __global__ void __launch_bounds__(kTcThreads, DUAL ? 2 : 1) wq_gemm_tc_kernel(co
 #pragma unroll
               for (int jw = 0; jw < 4; ++jw) {
                 const uint32_t w = ww[jw];
-                lo[2 * jw + 0] = lop3_and_or(w, kMask4, kMagic);
-                hi[2 * jw + 0] = lop3_and_or(__funnelshift_r(w, w, 4), kMask4, kMagicHi);
-                lo[2 * jw + 1] = lop3_and_or(__funnelshift_r(w, w, 8), kMask4, kMagic);
-                hi[2 * jw + 1] = lop3_and_or(__funnelshift_r(w, w, 12), kMask4, kMagicHi);
+                lo[2 * jw + 0] = lop3_and_or(w, kMask4, F::kMagic);
+                hi[2 * jw + 0] = lop3_and_or(__funnelshift_r(w, w, 4), kMask4, F::kMagicHi);
+                lo[2 * jw + 1] = lop3_and_or(__funnelshift_r(w, w, 8), kMask4, F::kMagic);
+                hi[2 * jw + 1] = lop3_and_or(__funnelshift_r(w, w, 12), kMask4, F::kMagicHi);
               }
               tc_st8(acol + c * 16, lo);
               tc_st8(acol + c * 16 + 8, hi);
@@ -660,11 +668,11 @@ __global__ void __launch_bounds__(kTcThreads, DUAL ? 2 : 1) wq_gemm_tc_kernel(co
           v[3] = apply_act<B2_ACT_SILU>(gv.w * p.alpha) * (uv.w * p.alpha);
           __nv_bfloat16* cp = p.C + (int64_t)m * p.ldc + nn;
           if (vec_ok && nn + 3 < p.N) {
-            *reinterpret_cast<uint2*>(cp) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+            *reinterpret_cast<uint2*>(cp) = make_uint2(F::pack(v[0], v[1]), F::pack(v[2], v[3]));
           } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-              if (nn + e < p.N) cp[e] = __float2bfloat16(v[e]);
+              if (nn + e < p.N) cp[e] = F::from_f(v[e]);
           }
         }
       } else if (p.act == B2_ACT_NONE && vec_ok && (p.N & 3) == 0 &&
@@ -690,16 +698,16 @@ __global__ void __launch_bounds__(kTcThreads, DUAL ? 2 : 1) wq_gemm_tc_kernel(co
             float v0 = a.x * p.alpha, v1 = a.y * p.alpha, v2 = a.z * p.alpha, v3 = a.w * p.alpha;
             if (p.bias) {
               const uint2 bv = __ldg(reinterpret_cast<const uint2*>(p.bias + nn));
-              v0 += bf16_lo(bv.x); v1 += bf16_hi(bv.x); v2 += bf16_lo(bv.y); v3 += bf16_hi(bv.y);
+              v0 += F::lo(bv.x); v1 += F::hi(bv.x); v2 += F::lo(bv.y); v3 += F::hi(bv.y);
             }
-            v0 += bf16_lo(res[j].x); v1 += bf16_hi(res[j].x); v2 += bf16_lo(res[j].y); v3 += bf16_hi(res[j].y);
-            const uint2 st2 = make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, v3));
+            v0 += F::lo(res[j].x); v1 += F::hi(res[j].x); v2 += F::lo(res[j].y); v3 += F::hi(res[j].y);
+            const uint2 st2 = make_uint2(F::pack(v0, v1), F::pack(v2, v3));
             *reinterpret_cast<uint2*>(p.C + (int64_t)m * p.ldc + nn) = st2;
             if (p.xg_out) {  // the next RMSNorm's scaled input and row statistics, from the values as stored (bf16)
-              const float r0 = bf16_lo(st2.x), r1 = bf16_hi(st2.x), r2 = bf16_lo(st2.y), r3 = bf16_hi(st2.y);
+              const float r0 = F::lo(st2.x), r1 = F::hi(st2.x), r2 = F::lo(st2.y), r3 = F::hi(st2.y);
               const uint2 gv = __ldg(reinterpret_cast<const uint2*>(p.gamma_out + nn));
               *reinterpret_cast<uint2*>(p.xg_out + (int64_t)m * p.ldxg + nn) =
-                  make_uint2(pack_bf16x2(r0 * bf16_lo(gv.x), r1 * bf16_hi(gv.x)), pack_bf16x2(r2 * bf16_lo(gv.y), r3 * bf16_hi(gv.y)));
+                  make_uint2(F::pack(r0 * F::lo(gv.x), r1 * F::hi(gv.x)), F::pack(r2 * F::lo(gv.y), r3 * F::hi(gv.y)));
               ssq = (r0 * r0 + r1 * r1) + (r2 * r2 + r3 * r3);
             }
           }
@@ -720,22 +728,22 @@ __global__ void __launch_bounds__(kTcThreads, DUAL ? 2 : 1) wq_gemm_tc_kernel(co
           float v0 = fs[m * kBN + np * 2] * p.alpha, v1 = fs[m * kBN + np * 2 + 1] * p.alpha;
           const bool has1 = (nn + 1) < p.N;
           if (p.bias) {
-            v0 += __bfloat162float(p.bias[nn]);
-            if (has1) v1 += __bfloat162float(p.bias[nn + 1]);
+            v0 += F::to_f(p.bias[nn]);
+            if (has1) v1 += F::to_f(p.bias[nn + 1]);
           }
           v0 = apply_act_rt(v0, p.act);
           v1 = apply_act_rt(v1, p.act);
           __nv_bfloat16* cp = p.C + (int64_t)m * p.ldc + nn;
           if (p.residual) {
             const __nv_bfloat16* rp = p.residual + (int64_t)m * p.ldc + nn;
-            v0 += __bfloat162float(rp[0]);
-            if (has1) v1 += __bfloat162float(rp[1]);
+            v0 += F::to_f(rp[0]);
+            if (has1) v1 += F::to_f(rp[1]);
           }
           if (has1 && ((reinterpret_cast<uintptr_t>(cp) & 3) == 0)) {
-            *reinterpret_cast<uint32_t*>(cp) = pack_bf16x2(v0, v1);
+            *reinterpret_cast<uint32_t*>(cp) = F::pack(v0, v1);
           } else {
-            cp[0] = __float2bfloat16(v0);
-            if (has1) cp[1] = __float2bfloat16(v1);
+            cp[0] = F::from_f(v0);
+            if (has1) cp[1] = F::from_f(v1);
           }
         }
       }
@@ -780,11 +788,21 @@ cudaError_t tc_configure(int wbits) {
   if (wbits == 4) {
     cfg2(wq_gemm_tc_kernel<4, false, false, false, true>); cfg2(wq_gemm_tc_kernel<4, true, false, false, true>);
     cfg2(wq_gemm_tc_kernel<4, false, false, true, true>); cfg2(wq_gemm_tc_kernel<4, true, false, true, true>);
+    cfg2(wq_gemm_tc_kernel<4, false, false, false, true, true>); cfg2(wq_gemm_tc_kernel<4, true, false, false, true, true>);
+    cfg2(wq_gemm_tc_kernel<4, false, false, true, true, true>); cfg2(wq_gemm_tc_kernel<4, true, false, true, true, true>);
     cfg(wq_gemm_tc_kernel<4, false>); cfg(wq_gemm_tc_kernel<4, true>); cfg(wq_gemm_tc_kernel<4, false, true>); cfg(wq_gemm_tc_kernel<4, true, true>);
     cfg(wq_gemm_tc_kernel<4, false, false, true>); cfg(wq_gemm_tc_kernel<4, true, false, true>);
+    cfg(wq_gemm_tc_kernel<4, false, false, false, false, true>); cfg(wq_gemm_tc_kernel<4, true, false, false, false, true>);
+    cfg(wq_gemm_tc_kernel<4, false, false, true, false, true>); cfg(wq_gemm_tc_kernel<4, true, false, true, false, true>);
   }
-  else if (wbits == 16) { cfg(wq_gemm_tc_kernel<16, false>); cfg(wq_gemm_tc_kernel<16, true>); }
-  else { cfg(wq_gemm_tc_kernel<8, false>); cfg(wq_gemm_tc_kernel<8, true>); }
+  else if (wbits == 16) {
+    cfg(wq_gemm_tc_kernel<16, false>); cfg(wq_gemm_tc_kernel<16, true>);
+    cfg(wq_gemm_tc_kernel<16, false, false, false, false, true>); cfg(wq_gemm_tc_kernel<16, true, false, false, false, true>);
+  }
+  else {
+    cfg(wq_gemm_tc_kernel<8, false>); cfg(wq_gemm_tc_kernel<8, true>);
+    cfg(wq_gemm_tc_kernel<8, false, false, false, false, true>); cfg(wq_gemm_tc_kernel<8, true, false, false, false, true>);
+  }
   return e;
 }
 
@@ -844,31 +862,40 @@ cudaError_t tc_launch(int wbits, const TcLaunch& a, cudaStream_t stream) {
   const int grid = (persist && units > cap) ? cap : units;
   const bool multi = units > grid;
   const size_t smem = (size_t)tc_smem_bytes(wbits, dual);
-  if (dual) {
-    if (a.group_tiles > 0)
-      return multi ? launch(wq_gemm_tc_kernel<4, true, false, true, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap)
-                   : launch(wq_gemm_tc_kernel<4, false, false, true, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap);
-    return multi ? launch(wq_gemm_tc_kernel<4, true, false, false, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap)
-                 : launch(wq_gemm_tc_kernel<4, false, false, false, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap);
-  }
+  auto go = [&](auto kern) { return launch(kern, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap); };
+  const bool g = a.group_tiles > 0, h = a.fp16;
   if (a8) {
-    if (wbits != 4) return cudaErrorNotSupported;
-    return multi ? launch(wq_gemm_tc_kernel<4, true, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap)
-                 : launch(wq_gemm_tc_kernel<4, false, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap);
+    if (wbits != 4 || h) return cudaErrorNotSupported;
+    return multi ? go(wq_gemm_tc_kernel<4, true, true>) : go(wq_gemm_tc_kernel<4, false, true>);
   }
-  if (a.group_tiles > 0) {
-    if (wbits != 4) return cudaErrorNotSupported;
-    return multi ? launch(wq_gemm_tc_kernel<4, true, false, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap)
-                 : launch(wq_gemm_tc_kernel<4, false, false, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap);
+  if (g && wbits != 4) return cudaErrorNotSupported;
+  if (wbits == 4) {
+    // (multi, grouped, dual, fp16)
+    switch ((multi ? 8 : 0) | (g ? 4 : 0) | (dual ? 2 : 0) | (h ? 1 : 0)) {
+      case 0: return go(wq_gemm_tc_kernel<4, false, false, false, false, false>);
+      case 1: return go(wq_gemm_tc_kernel<4, false, false, false, false, true>);
+      case 2: return go(wq_gemm_tc_kernel<4, false, false, false, true, false>);
+      case 3: return go(wq_gemm_tc_kernel<4, false, false, false, true, true>);
+      case 4: return go(wq_gemm_tc_kernel<4, false, false, true, false, false>);
+      case 5: return go(wq_gemm_tc_kernel<4, false, false, true, false, true>);
+      case 6: return go(wq_gemm_tc_kernel<4, false, false, true, true, false>);
+      case 7: return go(wq_gemm_tc_kernel<4, false, false, true, true, true>);
+      case 8: return go(wq_gemm_tc_kernel<4, true, false, false, false, false>);
+      case 9: return go(wq_gemm_tc_kernel<4, true, false, false, false, true>);
+      case 10: return go(wq_gemm_tc_kernel<4, true, false, false, true, false>);
+      case 11: return go(wq_gemm_tc_kernel<4, true, false, false, true, true>);
+      case 12: return go(wq_gemm_tc_kernel<4, true, false, true, false, false>);
+      case 13: return go(wq_gemm_tc_kernel<4, true, false, true, false, true>);
+      case 14: return go(wq_gemm_tc_kernel<4, true, false, true, true, false>);
+      default: return go(wq_gemm_tc_kernel<4, true, false, true, true, true>);
+    }
   }
-  if (wbits == 4)
-    return multi ? launch(wq_gemm_tc_kernel<4, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap)
-                 : launch(wq_gemm_tc_kernel<4, false>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap);
-  if (wbits == 16)
-    return multi ? launch(wq_gemm_tc_kernel<16, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap)
-                 : launch(wq_gemm_tc_kernel<16, false>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap);
-  return multi ? launch(wq_gemm_tc_kernel<8, true>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap)
-               : launch(wq_gemm_tc_kernel<8, false>, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap);
+  if (wbits == 16) {
+    if (h) return multi ? go(wq_gemm_tc_kernel<16, true, false, false, false, true>) : go(wq_gemm_tc_kernel<16, false, false, false, false, true>);
+    return multi ? go(wq_gemm_tc_kernel<16, true>) : go(wq_gemm_tc_kernel<16, false>);
+  }
+  if (h) return multi ? go(wq_gemm_tc_kernel<8, true, false, false, false, true>) : go(wq_gemm_tc_kernel<8, false, false, false, false, true>);
+  return multi ? go(wq_gemm_tc_kernel<8, true>) : go(wq_gemm_tc_kernel<8, false>);
 }
 
 }  // namespace b2

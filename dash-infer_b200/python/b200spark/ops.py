@@ -36,19 +36,22 @@ class Workspace:
 class GemmWQ:
     """GemmA16W4 / GemmA16W8 / dense Gemm (wbits 16) handle."""
 
-    def __init__(self, K, N, wbits, group_size=-1, max_m=64, signed=True, pair=False):
-        """pair=True: gate/up weight pair with a fused SwiGLU epilogue (N = intermediate size)."""
+    def __init__(self, K, N, wbits, group_size=-1, max_m=64, signed=True, pair=False, dtype=torch.bfloat16):
+        """pair=True: gate/up weight pair with a fused SwiGLU epilogue (N = intermediate size).
+        dtype: the activation / output / scale type FT of the handle (bf16 or fp16)."""
         self.K, self.N, self.wbits, self.group_size, self.max_m, self.pair = K, N, wbits, group_size, max_m, pair
+        self.dtype = dtype
         self.h = C.c_void_p()
         qtype = DT_U8 if wbits == 4 or not signed else DT_I8
-        d = GemmDesc(K, N, wbits, group_size if wbits != 16 else -1, DT_BF16, qtype, max_m, 1 if pair else 0)
+        ft = {torch.bfloat16: DT_BF16, torch.float16: _lib.DT_F16}[dtype]
+        d = GemmDesc(K, N, wbits, group_size if wbits != 16 else -1, ft, qtype, max_m, 1 if pair else 0)
         check(lib.b2_gemm_wq_create(C.byref(self.h), C.byref(d)), "b2_gemm_wq_create")
         self.bias = None
 
     def prepare(self, qdata, scales=None, zeros=None, bias=None):
         assert qdata.is_cuda and qdata.is_contiguous()
         if self.wbits != 16:
-            assert scales.dtype == torch.bfloat16 and zeros.dtype == torch.bfloat16
+            assert scales.dtype == self.dtype and zeros.dtype == self.dtype
             scales, zeros = scales.contiguous(), zeros.contiguous()
         check(lib.b2_gemm_wq_prepare_weights(self.h, _ptr(qdata), _ptr(scales), _ptr(zeros), None, _stream()),
               "b2_gemm_wq_prepare_weights")
@@ -84,9 +87,9 @@ class GemmWQ:
         if self.pair:
             act = _lib.ACT_SWIGLU
         M = a.numel() // a.shape[-1]
-        assert a.dtype == torch.bfloat16 and a.shape[-1] == self.K and a.stride(-1) == 1
+        assert a.dtype == self.dtype and a.shape[-1] == self.K and a.stride(-1) == 1
         if out is None:
-            out = torch.empty(*a.shape[:-1], self.N, dtype=torch.bfloat16, device=a.device)
+            out = torch.empty(*a.shape[:-1], self.N, dtype=self.dtype, device=a.device)
         wsb = ws.reserve(self.workspace_bytes(M))
         lda = a.stride(-2) if a.dim() > 1 else self.K
         ldc = out.stride(-2) if out.dim() > 1 else self.N

@@ -37,7 +37,7 @@ def test_param_validation_without_gpu():
     h = C.c_void_p()
     bad = _lib.GemmDesc(128, 128, 5, -1, _lib.DT_BF16, _lib.DT_U8, 8, 0)  # wbits 5
     assert lib.b2_gemm_wq_create(C.byref(h), C.byref(bad)) == 3
-    bad = _lib.GemmDesc(128, 128, 4, -1, _lib.DT_F16, _lib.DT_U8, 8, 0)  # fp16 not built yet -> unsupported
+    bad = _lib.GemmDesc(128, 128, 4, -1, _lib.DT_F32, _lib.DT_U8, 8, 0)  # FT is bf16 or fp16; fp32 activations -> unsupported
     assert lib.b2_gemm_wq_create(C.byref(h), C.byref(bad)) == 6
     bad = _lib.GemmDesc(128, 128, 4, -1, _lib.DT_BF16, _lib.DT_I8, 8, 0)  # A16W4 is uint4x2 only (gemm_a16w4.cpp:104-110)
     assert lib.b2_gemm_wq_create(C.byref(h), C.byref(bad)) == 3

@@ -13,19 +13,19 @@ pytestmark = pytest.mark.gpu
 TOL = 2e-2
 
 
-def _mk(K, N, M, seed, ft="bf16"):
+def _mk(K, N, M, seed, ft=torch.bfloat16):
     g = torch.Generator().manual_seed(seed)
-    w = (torch.randn(K, N, generator=g) * 0.02).to(torch.bfloat16)
-    a = (torch.rand(M, K, generator=g) * 2 - 1).to(torch.bfloat16)
+    w = (torch.randn(K, N, generator=g) * 0.02).to(ft)
+    a = (torch.rand(M, K, generator=g) * 2 - 1).to(ft)
     return w, a
 
 
-def _run(wbits, K, N, M, group, act=0, use_bias=False, use_res=False, alpha=1.0, seed=0, signed=True):
+def _run(wbits, K, N, M, group, act=0, use_bias=False, use_res=False, alpha=1.0, seed=0, signed=True, ft=torch.bfloat16):
     from b200spark import ops, quantize as PQ
-    w, a = _mk(K, N, M, seed)
+    w, a = _mk(K, N, M, seed, ft)
     g = torch.Generator().manual_seed(seed + 1)
-    bias = (torch.randn(N, generator=g) * 0.02).to(torch.bfloat16) if use_bias else None
-    res = (torch.randn(M, N, generator=g) * 0.1).to(torch.bfloat16) if use_res else None
+    bias = (torch.randn(N, generator=g) * 0.02).to(ft) if use_bias else None
+    res = (torch.randn(M, N, generator=g) * 0.1).to(ft) if use_res else None
     dev = "cuda"
     if wbits == 4:
         qd, s, z = PQ.quantize_a16w4(w, group)
@@ -35,7 +35,7 @@ def _run(wbits, K, N, M, group, act=0, use_bias=False, use_res=False, alpha=1.0,
         qu = qd.numpy()
     else:
         qd, s, z = w, None, None
-    op = ops.GemmWQ(K, N, wbits, group, max_m=max(M, 1), signed=signed)
+    op = ops.GemmWQ(K, N, wbits, group, max_m=max(M, 1), signed=signed, dtype=ft)
     op.prepare(qd.to(dev), s.to(dev) if s is not None else None, z.to(dev) if z is not None else None,
                bias.to(dev) if bias is not None else None)
     ws = ops.Workspace()
@@ -286,6 +286,49 @@ def test_tcgen05_rmsnorm_handoff(wbits, group, M):
         e_two = Q.err_min_abs_rel(ref, y_two.float().cpu().numpy())
         assert e_h <= (2 * TOL if pair else TOL), (e_h, e_two)
         assert e_h <= 2.0 * e_two + 2e-3, (e_h, e_two)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fp16 activations (the reference dispatches FLOAT16 first: gemm_a16w4_gpu.cpp:31-38, and most of its lowp tests are fp16:
+# tests/cpp/operator/cuda/operator_gemm_lowp_test.cpp:469-471).  Same kernels, the 16-bit type is a template parameter;
+# the exact-integer dequantisation uses 128 + q (fp16 has three more mantissa bits than bf16's 16 + q).
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M", [1, 3, 8, 16, 17, 31, 33, 64])
+@pytest.mark.parametrize("wbits,group", [(4, -1), (8, -1), (16, -1), (4, 128), (8, 64)])
+def test_fp16_all_paths(wbits, group, M):
+    """split-K GEMV (M <= 16), tcgen05 (M >= 17; sub-channel int8 stays on the mma.sync kernel), odd N, bias + residual"""
+    _run(wbits, 1024, 1023, M, group, use_bias=True, use_res=True, seed=wbits + M, ft=torch.float16)
+
+
+@pytest.mark.parametrize("K,N,M", [(3584, 4608, 1), (3584, 3584, 8), (18944, 3584, 16), (3584, 18944, 64), (18944, 3584, 64), (3584, 4608, 32)])
+def test_fp16_qwen2_7b_projections(K, N, M):
+    _run(4, K, N, M, -1, use_bias=(N == 4608), use_res=(N == 3584), seed=K % 89 + M, ft=torch.float16)
+    if M in (8, 64):
+        _run(8, K, N, M, -1, seed=K % 83 + M, signed=(M == 8), ft=torch.float16)
+
+
+@pytest.mark.parametrize("wbits,group,M", [(4, -1, 4), (4, -1, 64), (4, 128, 40), (8, -1, 20)])
+def test_fp16_swiglu_pair(wbits, group, M):
+    from b200spark import ops, quantize as PQ
+    K, N = 2048, 2944
+    g = torch.Generator().manual_seed(M * 3 + wbits)
+    ws_, refs = [], []
+    a = (torch.rand(M, K, generator=g) * 2 - 1).to(torch.float16)
+    for _ in range(2):
+        w = (torch.randn(K, N, generator=g) * 0.02).to(torch.float16)
+        if wbits == 4:
+            q, s, z = PQ.quantize_a16w4(w, group); qu = Q.unpack_u4x2(q.numpy(), N)
+        else:
+            q, s, z = PQ.quantize_a16w8(w, group); qu = q.numpy()
+        ws_.append((q, s, z))
+        refs.append(Q.gemm_wq_math(a.float().numpy(), qu, s.float().numpy(), z.float().numpy(), group).astype(np.float64))
+    op = ops.GemmWQ(K, N, wbits, group, max_m=M, pair=True, dtype=torch.float16)
+    op.prepare_swiglu(*[t.cuda() for t in ws_[0]], *[t.cuda() for t in ws_[1]])
+    out = op(a.cuda(), ops.Workspace())
+    torch.cuda.synchronize()
+    assert out.dtype == torch.float16
+    ref = (refs[0] / (1.0 + np.exp(-refs[0]))) * refs[1]
+    assert Q.err_min_abs_rel(ref.astype(np.float32), out.float().cpu().numpy()) <= TOL
 
 
 @pytest.mark.parametrize("wbits,group,M,N", [(4, -1, 1, 5117), (4, -1, 7, 5120), (8, -1, 16, 5117), (4, 128, 9, 5118), (16, -1, 3, 5117)])
