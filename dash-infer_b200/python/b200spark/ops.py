@@ -200,13 +200,16 @@ class SpanCache:
     """Test/bench stand-in for the reference's CacheSpanManager + SpannedVirtualCache: owns span pages for one
     layer's K and V of a batch and the device pointer tables [batch, max_spans] the kernels walk."""
 
-    def __init__(self, batch, max_len, n_heads, n_groups, span_len=128, quant_mode=KV_NONE, device="cuda", pool=None, fill=0, head=128):
+    def __init__(self, batch, max_len, n_heads, n_groups, span_len=128, quant_mode=KV_NONE, device="cuda", pool=None, fill=0, head=128,
+                 dtype=torch.bfloat16):
         """fill: byte the span pool is initialised with (the reference's span manager never zeroes frames; tests use
         0xFF = NaN patterns to prove no kernel consumes unwritten rows)."""
         self.batch, self.max_len = batch, max_len
         self.max_spans = (max_len + span_len - 1) // span_len
         self.head = head
-        self.cfg = SpanCfg(DT_BF16, quant_mode, n_heads, n_groups, head, span_len, self.max_spans, 0)
+        self.dtype = dtype  # FT of Q / the output / an unquantized cache
+        self.cfg = SpanCfg({torch.bfloat16: DT_BF16, torch.float16: _lib.DT_F16}[dtype], quant_mode, n_heads, n_groups, head, span_len,
+                           self.max_spans, 0)
         self.span_bytes = lib.b2_span_bytes(C.byref(self.cfg))
         assert self.span_bytes > 0, "bad span config"
         n = batch * self.max_spans
@@ -232,7 +235,7 @@ def cache_append(cache, qkv, old_lens, q_out=None, rope=None):
     cfg = cache.cfg
     B = qkv.shape[0]
     if q_out is None:
-        q_out = torch.empty(B, cfg.n_heads * cfg.head_size, dtype=torch.bfloat16, device=qkv.device)
+        q_out = torch.empty(B, cfg.n_heads * cfg.head_size, dtype=qkv.dtype, device=qkv.device)
     r = RopeCfg(float(rope[0]), int(rope[1]), 0) if rope is not None else None
     check(lib.b2_span_cache_append(C.byref(cfg), _ptr(cache.k_tab), _ptr(cache.v_tab), _ptr(q_out), _ptr(qkv),
                                    _ptr(old_lens), B, C.byref(r) if r is not None else None, _stream()),
@@ -243,7 +246,7 @@ def cache_append(cache, qkv, old_lens, q_out=None, rope=None):
 def context_copy(cache, which, b, src, seq_len=None):
     """Prefill: write sequence b's K (which='k') or V ('v') rows src [seq, ..., n_groups*128 leading values per token] into its
     spans (b2_span_context_copy).  src may be a strided view (e.g. the K part of a fused qkv tensor)."""
-    assert src.dtype == torch.bfloat16 and src.stride(-1) == 1
+    assert src.dtype == cache.dtype and src.stride(-1) == 1
     seq_len = src.shape[0] if seq_len is None else seq_len
     tab = cache.k_tab if which == "k" else cache.v_tab
     check(lib.b2_span_context_copy(C.byref(cache.cfg), C.c_void_p(tab.data_ptr() + b * cache.max_spans * 8), _ptr(src), src.stride(0),

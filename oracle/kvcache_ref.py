@@ -98,8 +98,9 @@ class SpanCacheRef:
     """One layer's K (or V) cache for a batch: a list of span byte buffers per sequence,
     byte-identical to what the reference's append kernel writes."""
 
-    def __init__(self, mode, span_len, n_groups, head=HEAD):
-        self.mode, self.span_len, self.n_groups, self.head = mode, span_len, n_groups, head
+    def __init__(self, mode, span_len, n_groups, head=HEAD, ft="bf16"):
+        """ft: the 16-bit type an unquantized cache stores ("bf16" or "fp16"; span::DataType FP16 / BF16)"""
+        self.mode, self.span_len, self.n_groups, self.head, self.ft = mode, span_len, n_groups, head, ft
         self.nbytes = span_bytes(mode, span_len, n_groups, head)
         self.spans = []  # list (per sequence) of list of np.uint8 arrays
 
@@ -119,7 +120,7 @@ class SpanCacheRef:
         buf = self.spans[b][si]
         if self.mode == QUANT_NONE:
             v = buf[: S * G * H * 2].view(np.uint16).reshape(G, S, H)
-            v[:, p, :] = bf16_bits(rows)
+            v[:, p, :] = bf16_bits(rows) if self.ft == "bf16" else np.asarray(rows, np.float32).astype(np.float16).view(np.uint16)
             return
         q, z, s = quant_rows(rows, self.mode)
         if self.mode == QUANT_I8:
@@ -142,7 +143,7 @@ class SpanCacheRef:
             n = min(S, length - si * S)
             if self.mode == QUANT_NONE:
                 v = buf[: S * G * H * 2].view(np.uint16).reshape(G, S, H)
-                out[:, si * S: si * S + n] = bits_to_f32(v[:, :n])
+                out[:, si * S: si * S + n] = bits_to_f32(v[:, :n]) if self.ft == "bf16" else v[:, :n].view(np.float16).astype(np.float32)
                 continue
             if self.mode == QUANT_I8:
                 q = buf[: S * G * H].view(np.int8).reshape(G, S, H)

@@ -16,14 +16,15 @@ def _bf16(x):
     return torch.from_numpy(x).to(torch.bfloat16)
 
 
-def _build(mode, B, lens, nH, nG, span, seed, max_len=None, fill=0, mirror=False):
+def _build(mode, B, lens, nH, nG, span, seed, max_len=None, fill=0, mirror=False, dtype=torch.bfloat16):
     # mirror=True keeps the oracle's OWN quantization of the same rows (append parity tests)
     """Fill a device SpanCache token by token with the product append kernel and mirror it in the oracle."""
     from b200spark import ops
     rng = np.random.default_rng(seed)
     max_len = max_len or (max(lens) + 1)
-    cache = ops.SpanCache(B, max_len, nH, nG, span, mode, fill=fill)
-    kref, vref = KV.SpanCacheRef(mode, span, nG), KV.SpanCacheRef(mode, span, nG)
+    cache = ops.SpanCache(B, max_len, nH, nG, span, mode, fill=fill, dtype=dtype)
+    ft = "fp16" if dtype == torch.float16 else "bf16"
+    kref, vref = KV.SpanCacheRef(mode, span, nG, ft=ft), KV.SpanCacheRef(mode, span, nG, ft=ft)
     for _ in range(B):
         kref.add_sequence(); vref.add_sequence()
     T = max(lens)
@@ -31,7 +32,7 @@ def _build(mode, B, lens, nH, nG, span, seed, max_len=None, fill=0, mirror=False
     q_last = np.zeros((B, nH, 128), np.float32)
     cur = torch.zeros(B, dtype=torch.int32, device="cuda")
     for t in range(T):
-        qkv = _bf16(rng.standard_normal((B, width)).astype(np.float32))
+        qkv = torch.from_numpy(rng.standard_normal((B, width)).astype(np.float32)).to(dtype)
         # sequences already at their final length keep re-writing a scratch position beyond their length
         pos = torch.tensor([min(t, lens[b]) for b in range(B)], dtype=torch.int32, device="cuda")
         q = ops.cache_append(cache, qkv.cuda(), pos)
@@ -254,3 +255,56 @@ def test_attention_piece_cap_env(monkeypatch):
     ref = KV.attention_ref(q, kref, vref, lens, nH, 1.0 / np.sqrt(128))
     for out in (out_tree, out_cap):
         assert np.abs(out.float().cpu().numpy().reshape(1, nH, 128) - ref).max() <= 6e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fp16 Q / output / unquantized cache (the reference's span-attention tests run FP16 first: span-attention/test/
+# test_quant_none.cpp); same kernels with the 16-bit type as a template parameter
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", [KV.QUANT_NONE, KV.QUANT_I8, KV.QUANT_U4])
+@pytest.mark.parametrize("span,nH,nG", [(16, 8, 2), (128, 28, 4), (64, 16, 1)])
+def test_attention_fp16(mode, span, nH, nG):
+    from b200spark import ops
+    lens = [1, 63, 64, 65, 200, 700]
+    B = len(lens)
+    cache, kref, vref, q = _build(mode, B, lens, nH, nG, span, seed=span + nH + 3 * mode, max_len=768, dtype=torch.float16)
+    attn = ops.SpanAttn(cache.cfg, B)
+    ws = ops.Workspace()
+    new_lens = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    qd = torch.from_numpy(q.reshape(B, -1)).to(torch.float16).cuda()
+    out = attn(qd, cache, new_lens, 768, ws)
+    out2 = attn(qd, cache, new_lens, 768, ws)
+    torch.cuda.synchronize()
+    assert out.dtype == torch.float16 and torch.equal(out, out2)
+    ref = KV.attention_ref(q, kref, vref, lens, nH, 1.0 / np.sqrt(128))
+    got = out.float().cpu().numpy().reshape(B, nH, 128)
+    # fp16 output / probabilities: 2^-10 relative envelope on top of the 2e-3 absolute bound
+    assert np.all(np.abs(got - ref) <= 2e-3 + 2.0 ** -9 * np.abs(ref)), float(np.abs(got - ref).max())
+
+
+def test_attention_fp16_long_ragged_with_rope():
+    """ctx 2048 / 4100 (split-KV partials, two-level merge) in fp16, rows appended through the fused-rotary path"""
+    from b200spark import ops
+    nH, nG, span = 28, 4, 128
+    lens = [2048, 4100, 777]
+    B = len(lens)
+    cache, kref, vref, q = _build(KV.QUANT_NONE, B, lens, nH, nG, span, seed=15, max_len=4224, dtype=torch.float16)
+    attn = ops.SpanAttn(cache.cfg, B)
+    new_lens = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    out = attn(torch.from_numpy(q.reshape(B, -1)).to(torch.float16).cuda(), cache, new_lens, 4224, ops.Workspace())
+    torch.cuda.synchronize()
+    ref = KV.attention_ref(q, kref, vref, lens, nH, 1.0 / np.sqrt(128))
+    assert np.abs(out.float().cpu().numpy().reshape(B, nH, 128) - ref).max() <= 3e-3
+    # fused rotary in fp16: against the fp32 NeoX formula rounded to fp16
+    rng = np.random.default_rng(3)
+    x = torch.from_numpy(rng.standard_normal((2, (nH + 2 * nG) * 128)).astype(np.float32)).to(torch.float16)
+    c2 = ops.SpanCache(2, 256, nH, nG, span, KV.QUANT_NONE, dtype=torch.float16)
+    pos = torch.tensor([5, 130], dtype=torch.int32, device="cuda")
+    qo = ops.cache_append(c2, x.cuda(), pos, rope=(1e6, 128))
+    torch.cuda.synchronize()
+    xf = x.float().numpy().reshape(2, nH + 2 * nG, 128)[:, :nH]
+    inv = 1e6 ** (-np.arange(64, dtype=np.float32) * 2 / 128)
+    ang = pos.cpu().numpy()[:, None].astype(np.float32) * inv[None, :]
+    cs, sn = np.cos(ang)[:, None, :], np.sin(ang)[:, None, :]
+    want = np.concatenate([xf[..., :64] * cs - xf[..., 64:] * sn, xf[..., 64:] * cs + xf[..., :64] * sn], -1)
+    assert np.abs(qo.float().cpu().numpy().reshape(2, nH, 128) - want).max() <= 4e-3
