@@ -7,8 +7,10 @@
 
 namespace b2 {
 
+template <bool H>
 __global__ void __launch_bounds__(256) rmsnorm_kernel(__nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ x,
                                                       const __nv_bfloat16* __restrict__ gamma, int cols, float eps) {
+  using F = Ft<H>;
   pdl_wait();
   pdl_launch_dependents();
   __shared__ float red[8];
@@ -17,7 +19,7 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(__nv_bfloat16* __restrict_
   float ss = 0.f;
   for (int i = threadIdx.x * 8; i < cols; i += 256 * 8) {
     const uint4 v = *reinterpret_cast<const uint4*>(xr + i);
-    const float f[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y), bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
+    const float f[8] = {F::lo(v.x), F::hi(v.x), F::lo(v.y), F::hi(v.y), F::lo(v.z), F::hi(v.z), F::lo(v.w), F::hi(v.w)};
 #pragma unroll
     for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
   }
@@ -33,10 +35,10 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(__nv_bfloat16* __restrict_
     const uint4 v = *reinterpret_cast<const uint4*>(xr + i);
     const uint4 gv = *reinterpret_cast<const uint4*>(gamma + i);
     uint4 o;
-    o.x = pack_bf16x2(bf16_lo(v.x) * inv * bf16_lo(gv.x), bf16_hi(v.x) * inv * bf16_hi(gv.x));
-    o.y = pack_bf16x2(bf16_lo(v.y) * inv * bf16_lo(gv.y), bf16_hi(v.y) * inv * bf16_hi(gv.y));
-    o.z = pack_bf16x2(bf16_lo(v.z) * inv * bf16_lo(gv.z), bf16_hi(v.z) * inv * bf16_hi(gv.z));
-    o.w = pack_bf16x2(bf16_lo(v.w) * inv * bf16_lo(gv.w), bf16_hi(v.w) * inv * bf16_hi(gv.w));
+    o.x = F::pack(F::lo(v.x) * inv * F::lo(gv.x), F::hi(v.x) * inv * F::hi(gv.x));
+    o.y = F::pack(F::lo(v.y) * inv * F::lo(gv.y), F::hi(v.y) * inv * F::hi(gv.y));
+    o.z = F::pack(F::lo(v.z) * inv * F::lo(gv.z), F::hi(v.z) * inv * F::hi(gv.z));
+    o.w = F::pack(F::lo(v.w) * inv * F::lo(gv.w), F::hi(v.w) * inv * F::hi(gv.w));
     *reinterpret_cast<uint4*>(y + (size_t)row * cols + i) = o;
   }
 }
@@ -179,8 +181,10 @@ __global__ void __launch_bounds__(128) rotary_kernel(__nv_bfloat16* __restrict__
   *reinterpret_cast<uint2*>(ptr) = make_uint2(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]));
 }
 
+template <bool H>
 __global__ void __launch_bounds__(256) binary_kernel(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ a,
                                                      const __nv_bfloat16* __restrict__ b, int64_t n, int op) {
+  using F = Ft<H>;
   pdl_wait();
   pdl_launch_dependents();
   const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 8;
@@ -190,15 +194,15 @@ __global__ void __launch_bounds__(256) binary_kernel(__nv_bfloat16* __restrict__
     uint32_t wo[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float l = op == B2_BIN_ADD ? bf16_lo(wa[j]) + bf16_lo(wb[j]) : bf16_lo(wa[j]) * bf16_lo(wb[j]);
-      const float h = op == B2_BIN_ADD ? bf16_hi(wa[j]) + bf16_hi(wb[j]) : bf16_hi(wa[j]) * bf16_hi(wb[j]);
-      wo[j] = pack_bf16x2(l, h);
+      const float l = op == B2_BIN_ADD ? F::lo(wa[j]) + F::lo(wb[j]) : F::lo(wa[j]) * F::lo(wb[j]);
+      const float h = op == B2_BIN_ADD ? F::hi(wa[j]) + F::hi(wb[j]) : F::hi(wa[j]) * F::hi(wb[j]);
+      wo[j] = F::pack(l, h);
     }
     *reinterpret_cast<uint4*>(out + i) = make_uint4(wo[0], wo[1], wo[2], wo[3]);
   } else {
     for (int64_t j = i; j < n; ++j) {
-      const float x = __bfloat162float(a[j]), y = __bfloat162float(b[j]);
-      out[j] = __float2bfloat16(op == B2_BIN_ADD ? x + y : x * y);
+      const float x = F::to_f(a[j]), y = F::to_f(b[j]);
+      out[j] = F::from_f(op == B2_BIN_ADD ? x + y : x * y);
     }
   }
 }
@@ -214,6 +218,7 @@ __global__ void __launch_bounds__(128) embedding_kernel(__nv_bfloat16* __restric
 }
 
 // greedy sampling: lowest index among the maxima (bit-exact index contract)
+template <bool H>
 __global__ void __launch_bounds__(1024) argmax_kernel(int64_t* __restrict__ ids_out, float* __restrict__ vals_out,
                                                       const __nv_bfloat16* __restrict__ logits, int n, int64_t ld, int64_t id_offset) {
   pdl_wait();
@@ -225,7 +230,7 @@ __global__ void __launch_bounds__(1024) argmax_kernel(int64_t* __restrict__ ids_
   float best = -INFINITY;
   int bi = 0x7fffffff;
   for (int i = threadIdx.x; i < n; i += 1024) {
-    const float v = __bfloat162float(row[i]);
+    const float v = Ft<H>::to_f(row[i]);
     if (v > best || (v == best && i < bi)) { best = v; bi = i; }
   }
 #pragma unroll
@@ -289,12 +294,19 @@ using namespace b2;
 
 extern "C" {
 
-int b2_rmsnorm(void* y, const void* x, const void* gamma, int rows, int cols, float eps, void* stream) {
+int b2_rmsnorm_ft(void* y, const void* x, const void* gamma, int rows, int cols, float eps, int ft, void* stream) {
   if (!y || !x || !gamma || rows <= 0 || cols <= 0) return B2_ERR_PARAM;
-  if (cols % 8) return B2_ERR_UNSUPPORTED;
-  B2_LAUNCH_CHECK("rmsnorm", launch(rmsnorm_kernel, dim3(rows), dim3(256), 0, (cudaStream_t)stream, true, (__nv_bfloat16*)y,
-                                    (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma, cols, eps));
+  if (cols % 8 || (ft != B2_DT_BF16 && ft != B2_DT_F16)) return B2_ERR_UNSUPPORTED;
+  if (ft == B2_DT_F16)
+    B2_LAUNCH_CHECK("rmsnorm", launch(rmsnorm_kernel<true>, dim3(rows), dim3(256), 0, (cudaStream_t)stream, true, (__nv_bfloat16*)y,
+                                      (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma, cols, eps));
+  else
+    B2_LAUNCH_CHECK("rmsnorm", launch(rmsnorm_kernel<false>, dim3(rows), dim3(256), 0, (cudaStream_t)stream, true, (__nv_bfloat16*)y,
+                                      (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma, cols, eps));
   return B2_OK;
+}
+int b2_rmsnorm(void* y, const void* x, const void* gamma, int rows, int cols, float eps, void* stream) {
+  return b2_rmsnorm_ft(y, x, gamma, rows, cols, eps, B2_DT_BF16, stream);
 }
 
 int b2_quant_fp8(void* y, int64_t ldy, float* scale, float* tile_sums, const void* x, const void* gamma, int rows, int cols,
@@ -316,13 +328,20 @@ int b2_rotary(void* qkv, const int32_t* pos, int batch, int n_heads, int n_group
   return B2_OK;
 }
 
-int b2_binary(void* out, const void* a, const void* b, int64_t n, int op, void* stream) {
+int b2_binary_ft(void* out, const void* a, const void* b, int64_t n, int op, int ft, void* stream) {
   if (!out || !a || !b || n <= 0) return B2_ERR_PARAM;
-  if (op != B2_BIN_ADD && op != B2_BIN_MUL) return B2_ERR_UNSUPPORTED;
+  if ((op != B2_BIN_ADD && op != B2_BIN_MUL) || (ft != B2_DT_BF16 && ft != B2_DT_F16)) return B2_ERR_UNSUPPORTED;
   const int64_t blocks = (n + 2047) / 2048;
-  B2_LAUNCH_CHECK("binary", launch(binary_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, true,
-                                   (__nv_bfloat16*)out, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, n, op));
+  if (ft == B2_DT_F16)
+    B2_LAUNCH_CHECK("binary", launch(binary_kernel<true>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, true,
+                                     (__nv_bfloat16*)out, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, n, op));
+  else
+    B2_LAUNCH_CHECK("binary", launch(binary_kernel<false>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, true,
+                                     (__nv_bfloat16*)out, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, n, op));
   return B2_OK;
+}
+int b2_binary(void* out, const void* a, const void* b, int64_t n, int op, void* stream) {
+  return b2_binary_ft(out, a, b, n, op, B2_DT_BF16, stream);
 }
 
 int b2_embedding(void* out, const void* table, const int64_t* ids, int batch, int hidden, void* stream) {
@@ -333,19 +352,27 @@ int b2_embedding(void* out, const void* table, const int64_t* ids, int batch, in
   return B2_OK;
 }
 
-int b2_argmax(int64_t* ids_out, const void* logits, int batch, int n, int64_t ld, void* stream) {
+int b2_argmax_ft(int64_t* ids_out, float* vals_out, const void* logits, int batch, int n, int64_t ld, int64_t id_offset, int ft,
+                 void* stream) {
   if (!ids_out || !logits || batch <= 0 || n <= 0) return B2_ERR_PARAM;
-  B2_LAUNCH_CHECK("argmax", launch(argmax_kernel, dim3(batch), dim3(1024), 0, (cudaStream_t)stream, true, ids_out, (float*)nullptr,
-                                   (const __nv_bfloat16*)logits, n, ld, (int64_t)0));
+  if (ft != B2_DT_BF16 && ft != B2_DT_F16) return B2_ERR_UNSUPPORTED;
+  if (ft == B2_DT_F16)
+    B2_LAUNCH_CHECK("argmax", launch(argmax_kernel<true>, dim3(batch), dim3(1024), 0, (cudaStream_t)stream, true, ids_out, vals_out,
+                                     (const __nv_bfloat16*)logits, n, ld, id_offset));
+  else
+    B2_LAUNCH_CHECK("argmax", launch(argmax_kernel<false>, dim3(batch), dim3(1024), 0, (cudaStream_t)stream, true, ids_out, vals_out,
+                                     (const __nv_bfloat16*)logits, n, ld, id_offset));
   return B2_OK;
+}
+
+int b2_argmax(int64_t* ids_out, const void* logits, int batch, int n, int64_t ld, void* stream) {
+  return b2_argmax_ft(ids_out, nullptr, logits, batch, n, ld, 0, B2_DT_BF16, stream);
 }
 
 int b2_argmax_shard(int64_t* ids_out, float* vals_out, const void* logits, int batch, int n, int64_t ld, int64_t id_offset,
                     void* stream) {
-  if (!ids_out || !vals_out || !logits || batch <= 0 || n <= 0) return B2_ERR_PARAM;
-  B2_LAUNCH_CHECK("argmax_shard", launch(argmax_kernel, dim3(batch), dim3(1024), 0, (cudaStream_t)stream, true, ids_out, vals_out,
-                                         (const __nv_bfloat16*)logits, n, ld, id_offset));
-  return B2_OK;
+  if (!vals_out) return B2_ERR_PARAM;
+  return b2_argmax_ft(ids_out, vals_out, logits, batch, n, ld, id_offset, B2_DT_BF16, stream);
 }
 
 int b2_argmax_merge(int64_t* ids_out, const float* all_vals, const int64_t* all_ids, int nranks, int batch, void* stream) {

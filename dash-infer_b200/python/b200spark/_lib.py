@@ -16,6 +16,7 @@ SYMBOLS = [
     "b2_span_bytes", "b2_span_cache_append", "b2_span_context_copy", "b2_span_attn_create", "b2_span_attn_destroy",
     "b2_span_attn_workspace_bytes", "b2_span_attn_run", "b2_span_attn_algo_bytes",
     "b2_rmsnorm", "b2_rotary", "b2_binary", "b2_embedding", "b2_argmax", "b2_argmax_shard", "b2_argmax_merge", "b2_lens_add",
+    "b2_rmsnorm_ft", "b2_binary_ft", "b2_argmax_ft",
     "b2_comm_create", "b2_comm_destroy", "b2_comm_buffer_bytes", "b2_comm_export", "b2_comm_connect", "b2_comm_connect_pointers",
     "b2_comm_local_buffer", "b2_comm_error", "b2_allreduce", "b2_allgather", "b2_gemm_wq_run_allreduce",
 ]
@@ -88,6 +89,9 @@ def _load():
         "b2_span_attn_run": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, vp, sz, f32, vp]),
         "b2_span_attn_algo_bytes": (sz, [C.POINTER(SpanCfg), i64]),
         "b2_rmsnorm": (i32, [vp, vp, vp, i32, i32, f32, vp]),
+        "b2_rmsnorm_ft": (i32, [vp, vp, vp, i32, i32, f32, i32, vp]),
+        "b2_binary_ft": (i32, [vp, vp, vp, i64, i32, i32, vp]),
+        "b2_argmax_ft": (i32, [vp, vp, vp, i32, i32, i64, i64, i32, vp]),
         "b2_rotary": (i32, [vp, vp, i32, i32, i32, i32, C.POINTER(RopeCfg), vp]),
         "b2_binary": (i32, [vp, vp, vp, i64, i32, vp]),
         "b2_embedding": (i32, [vp, vp, vp, i32, i32, vp]),

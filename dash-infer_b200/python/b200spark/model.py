@@ -42,8 +42,11 @@ TINY = ModelConfig("tiny-2L", 512, 8, 2, 1024, 2, 1024)
 KV_MODES = {"none": KV_NONE, "bf16": KV_NONE, "i8": KV_I8, "u4": KV_U4}
 
 
+_DT = torch.bfloat16  # the model dtype FT while a DecodeStack is being built (DecodeStack(dtype=...): bf16 or fp16)
+
+
 def synth_weight(K, N, gen, device, std=0.02):
-    return (torch.randn(K, N, generator=gen, device=device, dtype=torch.float32) * std).to(torch.bfloat16)
+    return (torch.randn(K, N, generator=gen, device=device, dtype=torch.float32) * std).to(_DT)
 
 
 class QuantLinear:
@@ -52,7 +55,7 @@ class QuantLinear:
 
     def __init__(self, K, N, wbits, group, gen, device, max_m, bias=False, keep_ref=False, shard=None):
         w = synth_weight(K, N, gen, device)
-        b = (torch.randn(N, generator=gen, device=device) * 0.02).to(torch.bfloat16) if bias else None
+        b = (torch.randn(N, generator=gen, device=device) * 0.02).to(_DT) if bias else None
         if wbits == 4:
             q, s, z = PQ.quantize_a16w4(w, group)
         elif wbits == 8:
@@ -73,7 +76,7 @@ class QuantLinear:
                 if shard[1] != 0:
                     b = None  # a row-split bias is added once (rank 0)
         self.K, self.N, self.wbits = K, N, wbits
-        self.op = ops.GemmWQ(K, N, wbits, group, max_m=max_m)
+        self.op = ops.GemmWQ(K, N, wbits, group, max_m=max_m, dtype=_DT)
         self.op.prepare(q.contiguous(), s, z, b)
 
     def __call__(self, x, ws, **kw):
@@ -103,7 +106,7 @@ class SwiGLULinear:
         if shard is not None:
             N = sum(e - a for a, e in shard[1])
         self.K, self.N = K, N
-        self.op = ops.GemmWQ(K, N, wbits, group, max_m=max_m, pair=True)
+        self.op = ops.GemmWQ(K, N, wbits, group, max_m=max_m, pair=True, dtype=_DT)
         self.op.prepare_swiglu(*qs[0], *qs[1])
 
     def __call__(self, x, ws, **kw):
@@ -120,10 +123,14 @@ class _RefView:
 class DecodeStack:
     def __init__(self, cfg, batch, max_len, wbits=4, group=-1, kv="none", span=128, seed=1234, device="cuda",
                  keep_ref=False, layers=None, tp_rank=0, tp_size=1, tp_group=None, fuse_swiglu=True, fuse_norm=False,
-                 collective=None, comm=None):
+                 collective=None, comm=None, dtype=torch.bfloat16):
         """tp_size > 1: the reference's tensor-parallel layout (QKV/gate/up column split, o/down row split + all-reduce,
         vocab-split lm_head + B-element all-gather); every rank builds the SAME full synthetic weights from `seed` and
         keeps its shard, exactly like the reference splits an already-quantized checkpoint."""
+        global _DT
+        assert dtype in (torch.bfloat16, torch.float16) and (dtype == torch.bfloat16 or (tp_size == 1 and cfg.head == 128)), \
+            "fp16: single GPU, head size 128 (the communicator and the head-64 kernels are bf16)"
+        self.dtype = _DT = dtype
         self.cfg, self.B, self.max_len = cfg, batch, max_len
         self.tp_rank, self.tp, self.tp_group = tp_rank, tp_size, tp_group
         # tensor-parallel exchange: "fused" = all-reduce inside the row-parallel GEMV's epilogue (b2_gemm_wq_run_allreduce;
@@ -150,11 +157,11 @@ class DecodeStack:
         self.layers = []
         for _ in range(self.n_layers):
             L = {}
-            L["g1"] = (1.0 + 0.1 * torch.randn(H, generator=gen, device=device)).to(torch.bfloat16)
+            L["g1"] = (1.0 + 0.1 * torch.randn(H, generator=gen, device=device)).to(_DT)
             L["qkv"] = QuantLinear(H, (nH + 2 * nG) * hd, wbits, group, gen, device, batch, bias=cfg.qkv_bias, keep_ref=keep_ref,
                                    shard=col_qkv)
             L["o"] = QuantLinear(nH * hd, H, wbits, group, gen, device, batch, keep_ref=keep_ref, shard=row)
-            L["g2"] = (1.0 + 0.1 * torch.randn(H, generator=gen, device=device)).to(torch.bfloat16)
+            L["g2"] = (1.0 + 0.1 * torch.randn(H, generator=gen, device=device)).to(_DT)
             if fuse_swiglu:
                 L["gateup"] = SwiGLULinear(H, I, wbits, group, gen, device, batch, keep_ref=keep_ref, shard=col_i)
                 if keep_ref:
@@ -163,9 +170,9 @@ class DecodeStack:
                 L["gate"] = QuantLinear(H, I, wbits, group, gen, device, batch, keep_ref=keep_ref, shard=col_i)
                 L["up"] = QuantLinear(H, I, wbits, group, gen, device, batch, keep_ref=keep_ref, shard=col_i)
             L["down"] = QuantLinear(I, H, wbits, group, gen, device, batch, keep_ref=keep_ref, shard=row)
-            L["cache"] = ops.SpanCache(batch, max_len, nHl, nGl, span, self.kv_mode, device, head=hd)
+            L["cache"] = ops.SpanCache(batch, max_len, nHl, nGl, span, self.kv_mode, device, head=hd, dtype=dtype)
             self.layers.append(L)
-        self.gf = (1.0 + 0.1 * torch.randn(H, generator=gen, device=device)).to(torch.bfloat16)
+        self.gf = (1.0 + 0.1 * torch.randn(H, generator=gen, device=device)).to(_DT)
         self.vocab_l = cfg.vocab // tp
         self.lm_head = QuantLinear(H, cfg.vocab, 16, -1, gen, device, batch, keep_ref=keep_ref,
                                    shard=("cols", TP.col_range_even(cfg.vocab, r, tp)) if tp > 1 else None)
@@ -178,7 +185,7 @@ class DecodeStack:
         self._lens_new = torch.ones(batch, dtype=torch.int32, device=device)
         self._ids = torch.zeros(batch, dtype=torch.int64, device=device)
         self._next_ids = torch.zeros(batch, dtype=torch.int64, device=device)
-        bf = dict(dtype=torch.bfloat16, device=device)
+        bf = dict(dtype=_DT, device=device)
         self._bufs = dict(x=torch.empty(batch, H, **bf), xn=torch.empty(batch, H, **bf),
                           qkv=torch.empty(batch, (nHl + 2 * nGl) * hd, **bf), q=torch.empty(batch, nHl * hd, **bf),
                           ao=torch.empty(batch, nHl * hd, **bf), gate=torch.empty(batch, self.I_l, **bf),
@@ -242,12 +249,12 @@ class DecodeStack:
             pos = torch.zeros(self.Bmax, dtype=torch.int32, device=self.device)
             width = (self.nH_l + 2 * nG) * self.head
             for t in range(ctx):
-                rows = torch.randn(self.Bmax, width, generator=gen, device=self.device).to(torch.bfloat16)
+                rows = torch.randn(self.Bmax, width, generator=gen, device=self.device).to(self.dtype)
                 for L in self.layers:
                     ops.cache_append(L["cache"], rows, pos, q_out=self._bufs["q"])
                 pos += 1
         for b in range(self.Bmax if self.head == 128 else 0):
-            rows = torch.randn(ctx, kw + vw, generator=gen, device=self.device).to(torch.bfloat16)
+            rows = torch.randn(ctx, kw + vw, generator=gen, device=self.device).to(self.dtype)
             for L in self.layers:
                 ops.context_copy(L["cache"], "k", b, rows[:, :kw])
                 ops.context_copy(L["cache"], "v", b, rows[:, kw:])

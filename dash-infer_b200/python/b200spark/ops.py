@@ -33,6 +33,11 @@ class Workspace:
         return self.buf
 
 
+def _ft(t):
+    """B2 dtype code of a 16-bit tensor (the FT of the glue ops)"""
+    return {torch.bfloat16: DT_BF16, torch.float16: _lib.DT_F16}[t.dtype]
+
+
 class GemmWQ:
     """GemmA16W4 / GemmA16W8 / dense Gemm (wbits 16) handle."""
 
@@ -288,7 +293,7 @@ class SpanAttn:
 def rmsnorm(x, gamma, eps=1e-6, out=None):
     out = torch.empty_like(x) if out is None else out
     cols = x.shape[-1]
-    check(lib.b2_rmsnorm(_ptr(out), _ptr(x), _ptr(gamma), x.numel() // cols, cols, float(eps), _stream()), "b2_rmsnorm")
+    check(lib.b2_rmsnorm_ft(_ptr(out), _ptr(x), _ptr(gamma), x.numel() // cols, cols, float(eps), _ft(x), _stream()), "b2_rmsnorm")
     return out
 
 
@@ -320,7 +325,7 @@ def rotary(qkv, pos, n_heads, n_groups, base=1e6, rotary_dim=128):
 
 def binary(a, b, op, out=None):
     out = torch.empty_like(a) if out is None else out
-    check(lib.b2_binary(_ptr(out), _ptr(a), _ptr(b), a.numel(), op, _stream()), "b2_binary")
+    check(lib.b2_binary_ft(_ptr(out), _ptr(a), _ptr(b), a.numel(), op, _ft(a), _stream()), "b2_binary")
     return out
 
 
@@ -334,7 +339,7 @@ def embedding(table, ids, out=None):
 def argmax(logits, out=None):
     B, n = logits.shape
     out = torch.empty(B, dtype=torch.int64, device=logits.device) if out is None else out
-    check(lib.b2_argmax(_ptr(out), _ptr(logits), B, n, logits.stride(0), _stream()), "b2_argmax")
+    check(lib.b2_argmax_ft(_ptr(out), None, _ptr(logits), B, n, logits.stride(0), 0, _ft(logits), _stream()), "b2_argmax")
     return out
 
 

@@ -230,6 +230,11 @@ size_t b2_span_attn_algo_bytes(const b2_span_cfg* cfg, int64_t total_tokens);
  * ===================================================================================== */
 /* y[r,:] = x[r,:] * rsqrt(mean(x^2) + eps) * gamma   (LayerNormNoBeta, layernorm.cu:86) */
 int b2_rmsnorm(void* y, const void* x, const void* gamma, int rows, int cols, float eps, void* stream);
+/* The glue ops with an explicit 16-bit type (ft = B2_DT_BF16 or B2_DT_F16); the unsuffixed entry points are the bf16 forms. */
+int b2_rmsnorm_ft(void* y, const void* x, const void* gamma, int rows, int cols, float eps, int ft, void* stream);
+int b2_binary_ft(void* out, const void* a, const void* b, int64_t n, int op, int ft, void* stream);
+int b2_argmax_ft(int64_t* ids_out, float* vals_out /* or NULL */, const void* logits, int batch, int n, int64_t ld, int64_t id_offset,
+                 int ft, void* stream);
 /* in-place NeoX rotary on the q and k heads of qkv [batch, (nH+2nG)*head]; position = pos[b] */
 int b2_rotary(void* qkv, const int32_t* pos, int batch, int n_heads, int n_groups, int head_size,
               const b2_rope_cfg* rope, void* stream);

@@ -22,18 +22,21 @@ from . import kvcache_ref as KV
 
 
 _EXACT = False  # set by RefDecoder(exact=True).step: no intermediate rounding at all (the "truth" both paths approximate)
+_FT = torch.bfloat16  # the model dtype every operator output is rounded to (set per RefDecoder: bf16 or fp16)
 
 
 def _bf(x):
-    return x.float() if _EXACT else x.to(torch.bfloat16)
+    return x.float() if _EXACT else x.to(_FT)
 
 
 class RefDecoder:
-    def __init__(self, cfg, layers, embed, gf, lm_head, kv_mode=KV.QUANT_NONE, exact=False):
+    def __init__(self, cfg, layers, embed, gf, lm_head, kv_mode=KV.QUANT_NONE, exact=False, ft=torch.bfloat16):
         """layers: list of dicts with g1,g2 (fp32 [H]) and qkv,o,gate,up,down = (W fp32 [K,N], bias or None).
         exact=True: the same graph on the same (bf16-valued) weights with fp32 activations and no rounding between operators —
         not a reference path, but the yardstick for "how far is a bf16 implementation from the exact result" on deep stacks."""
-        self.cfg, self.kv_mode, self.exact = cfg, kv_mode, exact
+        global _FT
+        self.cfg, self.kv_mode, self.exact, self.ft = cfg, kv_mode, exact, ft
+        _FT = ft
         self.embed = _bf(embed)
         self.gf = gf.float()
         self.lm = _bf(lm_head)
@@ -56,7 +59,8 @@ class RefDecoder:
 
     def _gemm(self, x, wb, act=None):
         w, b = wb
-        y = torch.matmul(_bf(x), w.float() if self.exact else w).float()
+        # fp32 accumulation of the rounded operands (fp16: through fp32 copies — the products are exact in fp32 either way)
+        y = (torch.matmul(_bf(x).float(), w.float()) if (self.exact or self.ft == torch.float16) else torch.matmul(_bf(x), w)).float()
         if b is not None:
             y = y + b
         if act == "silu":
@@ -82,12 +86,12 @@ class RefDecoder:
 
     def step(self, ids, pos):
         """ids: int64 [B]; pos[b]: tokens already cached.  Returns (logits fp32 [B, vocab], next_ids)."""
-        global _EXACT
-        _EXACT = self.exact
+        global _EXACT, _FT
+        _EXACT, _FT = self.exact, self.ft
         try:
             return self._step(ids, pos)
         finally:
-            _EXACT = False
+            _EXACT, _FT = False, torch.bfloat16
 
     def _step(self, ids, pos):
         cfg = self.cfg
@@ -118,7 +122,7 @@ class RefDecoder:
             h = _bf(g.float() * u.float())
             x = _bf(self._gemm(h, L["down"]).float() + x.float())
         xn = self._rms(x, self.gf)
-        logits = torch.matmul(xn, self.lm.float() if self.exact else self.lm).float()
+        logits = (torch.matmul(xn.float(), self.lm.float()) if (self.exact or self.ft == torch.float16) else torch.matmul(xn, self.lm)).float()
         return logits, torch.argmax(logits, dim=-1)
 
 
@@ -130,7 +134,8 @@ def from_stack(stack, kv_mode=KV.QUANT_NONE, exact=False):
         for k in ("qkv", "o", "gate", "up", "down"):
             d[k] = (L[k].ref, L[k].ref_bias)
         layers.append(d)
-    return RefDecoder(stack.cfg, layers, stack.embed.float().cpu(), stack.gf.float().cpu(), stack.lm_head.ref, kv_mode, exact=exact)
+    return RefDecoder(stack.cfg, layers, stack.embed.float().cpu(), stack.gf.float().cpu(), stack.lm_head.ref, kv_mode, exact=exact,
+                      ft=getattr(stack, "dtype", torch.bfloat16))
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -186,3 +186,34 @@ def test_config_c0_qwen2_0p5b_bf16_decode_parity():
         ids = enext  # all three follow the exact path's tokens: the caches stay comparable for all 128 steps
     assert st.lens_old.cpu().tolist() == [T]
     print("C0: worst |logit error| / logit range vs the exact graph: b200spark %.2e, reference CPU path (bf16) %.2e" % (worst_g, worst_r))
+
+
+@pytest.mark.parametrize("wbits,group,kv,B", [(4, -1, "none", 2), (8, -1, "i8", 2), (4, 128, "u4", 3), (4, -1, "none", 20)])
+def test_tiny_decoder_fp16(wbits, group, kv, B):
+    """The whole decode step in fp16 (activations, scales, unquantized cache, logits) against the oracle rounding to fp16
+    at the same points: split-K GEMV (B <= 16) and the tcgen05 GEMMs with the RMSNorm hand-off (B = 20), eager then a
+    captured graph."""
+    from b200spark import model
+    steps = 5
+    st = model.DecodeStack(model.TINY, B, 64, wbits=wbits, group=group, kv=kv, span=16, keep_ref=True, dtype=torch.float16)
+    assert st.logits.dtype == torch.float16
+    ref = DR.from_stack(st, {"none": KV.QUANT_NONE, "i8": KV.QUANT_I8, "u4": KV.QUANT_U4}[kv])
+    ref.reset(B)
+    ids = (torch.arange(B, dtype=torch.int64) * 37 + 3) % model.TINY.vocab
+    for t in range(steps):
+        if t == 3:
+            st.capture()
+        st.ids.copy_(ids.cuda())
+        nxt = st.step().cpu()
+        torch.cuda.synchronize()
+        glog = st.logits.float().cpu()
+        rlog, rnext = ref.step(ids, [t] * B)
+        tol = (4e-2 if kv == "u4" else 1e-2) * rlog.abs().max().item()
+        err = (glog - rlog).abs().max().item()
+        assert err <= tol, (t, err, tol)
+        assert torch.equal(nxt, torch.argmax(glog, dim=-1))
+        top2 = torch.topk(rlog, 2, dim=-1).values
+        for b in range(B):
+            if (top2[b, 0] - top2[b, 1]).item() > 2 * tol:
+                assert nxt[b].item() == rnext[b].item(), (t, b)
+        ids = nxt
