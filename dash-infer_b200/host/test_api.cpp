@@ -11,7 +11,16 @@
 
 using namespace allspark;
 
+// the 16-bit model dtype the test entry points below build their tensors with (BFLOAT16 unless as_test_set_dtype says FLOAT16)
+static allspark::DataType g_test_ft = allspark::DataType::BFLOAT16;
+
 extern "C" {
+int as_test_set_dtype(int dt) {
+  if (dt != (int)allspark::DataType::BFLOAT16 && dt != (int)allspark::DataType::FLOAT16) return -1;
+  g_test_ft = (allspark::DataType)dt;
+  return 0;
+}
+
 
 int as_test_registered(const char* op_type) {
   try {
@@ -28,7 +37,7 @@ static int run_gemm(const char* op_type, int M, int N, int K, int group_size, in
                     const void* residual_host, int binary_type, void* C_host) {
   try {
     CUDAContext ctx;
-    ctx.SetDtype(DataType::BFLOAT16);
+    ctx.SetDtype(g_test_ft);
     ctx.SetModelMaxBatch(M);
     TensorMap tensors, weights, weights_buffer;
     const std::string t = op_type;
@@ -39,29 +48,29 @@ static int run_gemm(const char* op_type, int M, int N, int K, int group_size, in
       if (src) ten->CopyDataFrom(src, ten->GetSizeInByte(), DeviceType::CPU);
       m[name] = ten;
     };
-    add(tensors, "input", DataType::BFLOAT16, Shape{1, M, K}, A_host);
+    add(tensors, "input", g_test_ft, Shape{1, M, K}, A_host);
     tensors["workspace"] = std::make_shared<AsTensor>("workspace", DeviceType::CUDA, DataType::INT8, DataMode::DENSE, Shape{0});
     const int G = group_size == -1 ? 1 : (K + group_size - 1) / group_size;
     if (wbits == 4) add(weights, "weight", (DataType)w_dtype, Shape{K, (N + 1) / 2}, w_host);
     else if (wbits == 8) add(weights, "weight", (DataType)w_dtype, Shape{K, N}, w_host);
-    else add(weights, "weight", DataType::BFLOAT16, Shape{K, N}, w_host);
+    else add(weights, "weight", g_test_ft, Shape{K, N}, w_host);
     OperatorProto proto;
     proto.op_type_ = t; proto.op_name_ = "test_" + t;
     proto.inputs_.push_back({"input"}); proto.outputs_.push_back({"output"});
     proto.weights_.push_back({"weight"});
     if (residual_host) {  // do_binary_add_fused graphs: Gemm(x, residual) with binary_type ADD (qwen_v15.py:280-286)
-      add(tensors, "residual", DataType::BFLOAT16, Shape{1, M, N}, residual_host);
+      add(tensors, "residual", g_test_ft, Shape{1, M, N}, residual_host);
       proto.inputs_.push_back({"residual"});
     }
     if (binary_type) proto.SetAttr<int>("binary_type", binary_type);
     if (quant) {
-      add(weights, "scales", DataType::BFLOAT16, Shape{G, N}, scales_host);
-      add(weights, "zeros", DataType::BFLOAT16, Shape{G, N}, zeros_host);
+      add(weights, "scales", g_test_ft, Shape{G, N}, scales_host);
+      add(weights, "zeros", g_test_ft, Shape{G, N}, zeros_host);
       proto.weights_.push_back({"scales"}); proto.weights_.push_back({"zeros"});
       if (group_size != -1) proto.SetAttr<int>("GroupSize", group_size);
     }
     if (bias_host) {
-      add(weights, "bias", DataType::BFLOAT16, Shape{N}, bias_host);
+      add(weights, "bias", g_test_ft, Shape{N}, bias_host);
       proto.weights_.push_back({"bias"});
     }
     proto.SetAttr<float>("alpha", alpha);
@@ -163,7 +172,7 @@ int as_test_span_attn(int batch, int steps, int n_heads, int n_groups, int span_
                       int layer_id, const void* qkv_all, void* out_all) {
   try {
     CUDAContext ctx;
-    ctx.SetDtype(DataType::BFLOAT16);
+    ctx.SetDtype(g_test_ft);
     ctx.SetModelMaxBatch(batch);
     ctx.SetModelMaxLength(max_len);
     ctx.SetNumberHeads(n_heads);
@@ -173,7 +182,7 @@ int as_test_span_attn(int batch, int steps, int n_heads, int n_groups, int span_
     auto cc = SpanCacheConfig::Create((AsCacheMode)cache_mode, span_len);
     if (!cc) return (int)AsStatus::ALLSPARK_PARAM_ERROR;
     ctx.SetCacheConfig(cc);
-    const size_t span_bytes = CacheUtils::GetSpanSizeInBytes(*cc, DataType::BFLOAT16, n_groups, 128);
+    const size_t span_bytes = CacheUtils::GetSpanSizeInBytes(*cc, g_test_ft, n_groups, 128);
     const int max_spans = (max_len + span_len - 1) / span_len;
     auto pool = std::make_shared<CacheSpanPool>(span_bytes, 2 * batch * layers * max_spans);
     RuntimeContext rt(false);
@@ -185,7 +194,7 @@ int as_test_span_attn(int batch, int steps, int n_heads, int n_groups, int span_
     }
     const int64_t W = (int64_t)(n_heads + 2 * n_groups) * 128, OW = (int64_t)n_heads * 128;
     TensorMap tensors, weights, weights_buffer;
-    tensors["qkv"] = std::make_shared<AsTensor>("qkv", DeviceType::CUDA, DataType::BFLOAT16, DataMode::DENSE, Shape{batch, 1, W});
+    tensors["qkv"] = std::make_shared<AsTensor>("qkv", DeviceType::CUDA, g_test_ft, DataMode::DENSE, Shape{batch, 1, W});
     tensors["workspace"] = std::make_shared<AsTensor>("workspace", DeviceType::CUDA, DataType::INT8, DataMode::DENSE, Shape{0});
     OperatorProto proto;
     // the layer index travels in the op name like in a serialized model ("decoder.layer.<i>.attention", common.h:239-257)

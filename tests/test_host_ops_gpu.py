@@ -27,6 +27,8 @@ def _lib():
     lib.as_test_allreduce.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
     lib.as_test_span_attn.restype = C.c_int
     lib.as_test_span_attn.argtypes = [C.c_int] * 9 + [C.c_void_p, C.c_void_p]
+    lib.as_test_set_dtype.restype = C.c_int
+    lib.as_test_set_dtype.argtypes = [C.c_int]
     lib.as_test_registered.restype = C.c_int
     lib.as_test_registered.argtypes = [C.c_char_p]
     return lib
@@ -219,3 +221,73 @@ def test_allreduce_operator(nranks):
     got = torch.from_numpy(out).view(torch.bfloat16)
     for r in range(nranks):
         assert torch.equal(got[r], exp), r
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("op,group,M", [("GemmA16W4", -1, 1), ("GemmA16W4", -1, 40), ("GemmA16W4", 128, 17), ("GemmA16W8", -1, 3),
+                                        ("GemmA16W8", 64, 9), ("Gemm", -1, 33)])
+def test_gemm_operators_fp16(op, group, M):
+    """FLOAT16 tensors through the same operator classes (the reference dispatches FLOAT16 first, gemm_a16w4_gpu.cpp:31-38)"""
+    from b200spark import quantize as PQ
+    lib = _lib()
+    K, N = 1024, 640
+    g = torch.Generator().manual_seed(M + len(op))
+    w = (torch.randn(K, N, generator=g) * 0.02).to(torch.float16)
+    a = (torch.rand(M, K, generator=g) * 2 - 1).to(torch.float16)
+    bias = (torch.randn(N, generator=g) * 0.02).to(torch.float16)
+    if op == "GemmA16W4":
+        q, s, z = PQ.quantize_a16w4(w, group); qu = Q.unpack_u4x2(q.numpy(), N); wdt = 10
+    elif op == "GemmA16W8":
+        q, s, z = PQ.quantize_a16w8(w, group); qu = q.numpy(); wdt = 3
+    else:
+        q, s, z = w, None, None; wdt = 2
+    f16 = lambda t: t.contiguous().view(torch.int16).numpy()
+    out = np.zeros((M, N), np.int16)
+    qn = f16(q) if op == "Gemm" else q.contiguous().numpy()
+    an, bn = f16(a), f16(bias)
+    sn, zn = (f16(s), f16(z)) if s is not None else (None, None)
+    assert lib.as_test_set_dtype(2) == 0
+    try:
+        rc = lib.as_test_gemm(op.encode(), M, N, K, group, 5, 1.0, an.ctypes.data, qn.ctypes.data, wdt,
+                              sn.ctypes.data if sn is not None else None, zn.ctypes.data if zn is not None else None,
+                              bn.ctypes.data, out.ctypes.data)
+    finally:
+        lib.as_test_set_dtype(9)
+    assert rc == 0, rc
+    got = torch.from_numpy(out).view(torch.float16).float().numpy()
+    if op == "Gemm":
+        ref = Q.activation((a.float().numpy().astype(np.float64) @ w.float().numpy().astype(np.float64)
+                            + bias.float().numpy()[None]).astype(np.float32), 5)
+    else:
+        ref = Q.gemm_wq_math(a.float().numpy(), qu, s.float().numpy(), z.float().numpy(), group, bias.float().numpy(), 5)
+    assert Q.err_min_abs_rel(ref, got) <= 2e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_span_attention_operator_fp16(mode):
+    lib = _lib()
+    B, nH, nG, span, steps = 2, 8, 2, 32, 70
+    W, OW = (nH + 2 * nG) * 128, nH * 128
+    rng = np.random.default_rng(77 + mode)
+    qkv = torch.from_numpy(rng.standard_normal((steps, B, W)).astype(np.float32)).to(torch.float16)
+    out = np.zeros((steps, B, OW), np.int16)
+    assert lib.as_test_set_dtype(2) == 0
+    try:
+        rc = lib.as_test_span_attn(B, steps, nH, nG, span, mode, 256, 3, 1, qkv.view(torch.int16).numpy().ctypes.data, out.ctypes.data)
+    finally:
+        lib.as_test_set_dtype(9)
+    assert rc == 0, rc
+    got = torch.from_numpy(out).view(torch.float16).float().numpy().reshape(steps, B, nH, 128)
+    kref, vref = KV.SpanCacheRef(mode, span, nG, ft="fp16"), KV.SpanCacheRef(mode, span, nG, ft="fp16")
+    for _ in range(B):
+        kref.add_sequence(); vref.add_sequence()
+    x = qkv.float().numpy().reshape(steps, B, nH + 2 * nG, 128)
+    for t in range(steps):
+        for b in range(B):
+            kref.append(b, t, x[t, b, nH:nH + nG]); vref.append(b, t, x[t, b, nH + nG:])
+        if t in (0, span - 1, span, steps - 1):
+            ref = KV.attention_ref(x[t, :, :nH], kref, vref, [t + 1] * B, nH, 1.0 / np.sqrt(128))
+            # quantized modes: the oracle quantizes with an IEEE reciprocal (ties can move a code by one step)
+            tol = 2e-3 + 2.0 ** -9 * np.abs(ref) + 0.1 * 8.0 * {0: 0.0, 1: 1 / 255, 2: 1 / 15}[mode]
+            assert np.all(np.abs(got[t] - ref) <= tol), (t, np.abs(got[t] - ref).max())
