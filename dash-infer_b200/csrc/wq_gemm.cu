@@ -844,6 +844,7 @@ struct Plan {
 struct b2_gemm_wq {
   b2_gemm_wq_desc d;
   int Kp = 0, Np = 0, KT = 0, NG = 0, G = 1, group_tiles = 0;
+  int group_k = 0;  // > 0: quantization group size that is not a multiple of 64 (params looked up per 8-k word)
   size_t tile_bytes = 0, packed_bytes = 0;
   void* packed = nullptr;
   bool own_packed = false;
@@ -1003,21 +1004,28 @@ int b2_gemm_wq_create(b2_gemm_wq_t* out, const b2_gemm_wq_desc* d) {
   if (d->wbits == 4 && d->qtype != B2_DT_U8) return B2_ERR_PARAM;  // gemm_a16w4.cpp:104-110: uint8(uint4x2) only
   if (d->wbits == 8 && d->qtype != B2_DT_U8 && d->qtype != B2_DT_I8) return B2_ERR_PARAM;
   if (d->K % 8 != 0) return B2_ERR_UNSUPPORTED;
+  bool general_groups = false;  // group sizes that do not divide the 64-k tile (reference: any multiple of 8 >= 32 through its
+                                // dequantize + cuBLAS path, gemm_a16w4.cpp:57-63): int4 only, tcgen05 kernel at every batch
   if (d->wbits != 16 && d->group_size != -1) {
-    if (d->group_size <= 0 || d->group_size % kBK != 0) return B2_ERR_UNSUPPORTED;
+    if (d->group_size <= 0) return B2_ERR_UNSUPPORTED;
+    if (d->group_size % kBK != 0) {
+      if (d->wbits != 4 || d->group_size % 8 != 0 || d->group_size < 32 || d->reserved == 1) return B2_ERR_UNSUPPORTED;
+      general_groups = true;
+    }
   }
   b2_gemm_wq* h = new (std::nothrow) b2_gemm_wq();
   if (!h) return B2_ERR_RUNTIME;
   h->d = *d;
   const bool grouped = d->wbits != 16 && d->group_size != -1;
-  const int kq = grouped ? d->group_size : kBK;
+  const int kq = (grouped && !general_groups) ? d->group_size : kBK;
   h->Kp = (d->K + kq - 1) / kq * kq;
   h->pair = d->reserved == 1;
   h->Np = h->pair ? (d->N + 63) / 64 * kBN : (d->N + kBN - 1) / kBN * kBN;  // pair: 64 gate + 64 up channels per tile
   h->KT = h->Kp / kBK;
   h->NG = h->Np / kBN;
-  h->group_tiles = grouped ? d->group_size / kBK : 0;
-  h->G = grouped ? h->Kp / d->group_size : 1;
+  h->group_tiles = (grouped && !general_groups) ? d->group_size / kBK : 0;
+  h->group_k = general_groups ? d->group_size : 0;
+  h->G = grouped ? (general_groups ? (d->K + d->group_size - 1) / d->group_size : h->Kp / d->group_size) : 1;
   h->tile_bytes = tile_bytes_of(d->wbits);
   h->packed_bytes = (size_t)h->NG * h->KT * h->tile_bytes;
   cudaGetDevice(&h->device);
@@ -1129,6 +1137,7 @@ static bool use_tc(const b2_gemm_wq* h, int M) {
   static const int min_m = env_int("B2_GEMM_TC_MIN_M", 17);
   static const int grouped = env_int("B2_GEMM_TC_GROUPED", 1);
   // int4 / int8 per-channel, dense bf16 (lm_head), and int4 sub-channel (the scale is applied to the weights in the dequant warps)
+  if (h->group_k > 0) return true;  // general group sizes exist on the tcgen05 kernel only
   return M >= min_m && (h->group_tiles == 0 || (grouped && h->d.wbits == 4));
 }
 
@@ -1205,7 +1214,7 @@ int b2_gemm_wq_run_fp8(b2_gemm_wq_t h, const void* A8, int64_t lda_bytes, const 
   if (!h || !A8 || !a_scale || !tile_sums || !C || M <= 0) return B2_ERR_PARAM;
   if (!h->packed) return B2_ERR_RUNTIME;
   if (M > h->d.max_m) return B2_ERR_LIMIT;
-  if (h->d.wbits != 4 || h->group_tiles > 0 || h->d.ft != B2_DT_BF16) return B2_ERR_UNSUPPORTED;  // int4 per-channel weights (the IQ default), bf16 outputs
+  if (h->d.wbits != 4 || h->group_tiles > 0 || h->group_k > 0 || h->d.ft != B2_DT_BF16) return B2_ERR_UNSUPPORTED;  // int4 per-channel weights (the IQ default), bf16 outputs
   if (h->pair != (activation == B2_ACT_SWIGLU)) return B2_ERR_PARAM;
   if (activation != B2_ACT_SWIGLU && (activation < 0 || activation > B2_ACT_SIGMOID)) return B2_ERR_PARAM;
   if (h->pair && (bias || residual)) return B2_ERR_UNSUPPORTED;
@@ -1275,6 +1284,7 @@ static int run_impl(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, int64_t
   }
   if (!h->packed) return B2_ERR_RUNTIME;
   if (M > h->d.max_m) return B2_ERR_LIMIT;
+  if (h->group_k > 0 && comm) return B2_ERR_UNSUPPORTED;
   if (h->pair != (activation == B2_ACT_SWIGLU)) return B2_ERR_PARAM;  // paired image <=> SwiGLU epilogue
   if (activation != B2_ACT_SWIGLU && (activation < 0 || activation > B2_ACT_SIGMOID)) return B2_ERR_PARAM;
   if (h->pair && (bias || residual)) return B2_ERR_UNSUPPORTED;
@@ -1301,6 +1311,7 @@ static int run_impl(b2_gemm_wq_t h, const void* A, int64_t lda, void* C, int64_t
       a.N = h->d.N; a.K = h->d.K; a.Np = h->Np; a.KT = h->KT; a.NG = h->NG; a.S = tcs;
       a.act = activation; a.alpha = alpha;
       a.group_tiles = h->group_tiles;
+      a.group_k = h->group_k; a.ngroups = h->G;
       if (fused) {
         a.norm_ld = M;
         if (fuse->norm_sumsq) {

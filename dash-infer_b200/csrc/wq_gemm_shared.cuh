@@ -38,6 +38,7 @@ struct TcLaunch {
   const float* a_scale = nullptr;    // != NULL: A is fp8-e4m3 in the b2 fp8 activation layout (lda in bytes)
   const float* tile_sums = nullptr;  // [M][KT] sums of the quantized activations per 64-k tile
   int group_tiles = 0;               // > 0: sub-channel weights, k-tiles per quantization group (sz is [G][Np])
+  int group_k = 0, ngroups = 1;      // group_k > 0: group size not a multiple of 64 (a multiple of 8): params per 8-k word
   bool fp16 = false;                 // activations / outputs / bias / residual are fp16 (else bf16)
   bool dual = false;                 // two CTAs per SM (int4 weights, bf16 activations): half-depth stages, 256 TMEM columns
   // RMSNorm hand-off between GEMMs (b2_gemm_fuse, batches >= 17).  Consumer: A holds bf16(x * gamma); the result rows are

@@ -155,6 +155,8 @@ struct TcParams {
   int64_t ldxg;
   int nm;           // MMA N (batch columns): 64, or 32 when M <= 32 (half the tensor-pipe time and activation traffic)
   int group_tiles;  // GROUPED instantiation: k-tiles per quantization group; sz is [G][Np]
+  int group_k, ngroups;  // GROUPED with a group size that is no multiple of 64 (a multiple of 8, >= 32): 8 consecutive k — one
+                         // word of the image — never straddle a group, so the params are looked up per word
   int dbg;  // ablation bitmask, only honoured when compiled with -DB2_TC_ABLATE (tools/tc_ablate.py)
 };
 
@@ -439,7 +441,7 @@ __global__ void __launch_bounds__(kTcThreads, DUAL ? 2 : 1) wq_gemm_tc_kernel(co
       const int slot = g % NSW, ab = g % NAB;
       // sub-channel weights: this stage's per-(group, channel) params are requested before the wait on the weights
       uint32_t gs2[TPS], gc2[TPS];
-      if (GROUPED) {
+      if (GROUPED && p.group_k == 0) {
 #pragma unroll
         for (int ti = 0; ti < TPS; ++ti) {
           const int kt = min(kt0 + st * TPS + ti, kt1 - 1);
@@ -491,15 +493,26 @@ __global__ void __launch_bounds__(kTcThreads, DUAL ? 2 : 1) wq_gemm_tc_kernel(co
                   a[4 * jw + 3] = lop3_and_or(__funnelshift_r(w, w, 12), kMask4, F::kMagic);
                 }
                 if (GROUPED) {  // (16 + q) - 24 = q - 8 exactly, then one fused multiply-add: (q - 8) s + (8 - z) s
+                  uint32_t sw[2] = {gs2[ti], gs2[ti]}, cw[2] = {gc2[ti], gc2[ti]};
+                  if (p.group_k > 0) {  // word j = 2h + jw of chunk c holds k = 64 kt + 32 c + 8 j + (0..7): one group per word
+#pragma unroll
+                    for (int jw = 0; jw < 2; ++jw) {
+                      const int k0 = (kt0 + st * TPS + ti) * kBK + 32 * c + 8 * (2 * h + jw);
+                      const float2 z = __ldg(p.sz + (size_t)min(k0 / p.group_k, p.ngroups - 1) * p.Np + ng * kBN + r);
+                      sw[jw] = F::pack(z.x, z.x);
+                      const float cc = (F::kBias + 8.f - z.y) * z.x;
+                      cw[jw] = F::pack(cc, cc);
+                    }
+                  }
 #pragma unroll
                   for (int e = 0; e < 8; ++e) {
                     uint32_t t2;
                     if (H) {  // (128 + q) - 136
                       asm("add.rn.f16x2 %0, %1, %2;" : "=r"(t2) : "r"(a[e]), "r"(0xD840D840u));
-                      asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(a[e]) : "r"(t2), "r"(gs2[ti]), "r"(gc2[ti]));
+                      asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(a[e]) : "r"(t2), "r"(sw[e >> 2]), "r"(cw[e >> 2]));
                     } else {
                       asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(t2) : "r"(a[e]), "r"(0xC1C0C1C0u));
-                      asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(a[e]) : "r"(t2), "r"(gs2[ti]), "r"(gc2[ti]));
+                      asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(a[e]) : "r"(t2), "r"(sw[e >> 2]), "r"(cw[e >> 2]));
                     }
                   }
                 }
@@ -846,7 +859,7 @@ cudaError_t tc_launch(int wbits, const TcLaunch& a, cudaStream_t stream) {
   p.a_scale = a.a_scale; p.tile_sums = a.tile_sums;
   p.norm_sumsq = a.norm_sumsq; p.norm_parts = a.norm_parts; p.norm_ld = a.norm_ld; p.norm_inv_hidden = a.norm_inv_hidden;
   p.norm_eps = a.norm_eps; p.sumsq_out = a.sumsq_out; p.xg_out = a.xg_out; p.gamma_out = a.gamma_out; p.ldxg = a.ldxg;
-  p.nm = nm; p.group_tiles = a.group_tiles;
+  p.nm = nm; p.group_tiles = a.group_tiles; p.group_k = a.group_k; p.ngroups = a.ngroups;
   p.dbg = 0;
 #ifdef B2_TC_ABLATE
   if (const char* e = getenv("B2_TC_ABLATE")) p.dbg = atoi(e);
@@ -863,7 +876,7 @@ cudaError_t tc_launch(int wbits, const TcLaunch& a, cudaStream_t stream) {
   const bool multi = units > grid;
   const size_t smem = (size_t)tc_smem_bytes(wbits, dual);
   auto go = [&](auto kern) { return launch(kern, dim3(grid), dim3(kTcThreads), smem, stream, true, p, amap); };
-  const bool g = a.group_tiles > 0, h = a.fp16;
+  const bool g = a.group_tiles > 0 || a.group_k > 0, h = a.fp16;
   if (a8) {
     if (wbits != 4 || h) return cudaErrorNotSupported;
     return multi ? go(wq_gemm_tc_kernel<4, true, true>) : go(wq_gemm_tc_kernel<4, false, true>);

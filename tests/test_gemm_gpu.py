@@ -331,6 +331,15 @@ def test_fp16_swiglu_pair(wbits, group, M):
     assert Q.err_min_abs_rel(ref.astype(np.float32), out.float().cpu().numpy()) <= TOL
 
 
+@pytest.mark.parametrize("ft", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("group,K,M", [(32, 1024, 1), (40, 1000, 5), (72, 2048, 16), (200, 1000, 33), (136, 4096, 100), (96, 3584, 64)])
+def test_general_group_sizes_w4(group, K, M, ft):
+    """Group sizes that do not divide the 64-k tile (the reference's dequantize + cuBLAS test draws any multiple of 8 in
+    [64, 512]: operator_gemm_lowp_test.cpp:893-903; gemm_a16w4.cpp:57-63 accepts >= 32): int4, on the tcgen05 kernel at
+    every batch, the (scale, zero) looked up per 8-k word of the weight image."""
+    _run(4, K, 1023, M, group, use_bias=True, use_res=(M > 16), seed=group + M, ft=ft)
+
+
 @pytest.mark.parametrize("wbits,group,M,N", [(4, -1, 1, 5117), (4, -1, 7, 5120), (8, -1, 16, 5117), (4, 128, 9, 5118), (16, -1, 3, 5117)])
 def test_cluster_split_k_epilogue(monkeypatch, wbits, group, M, N):
     """Shapes wide enough for the thread-block-cluster split-K (the k-slices of a tile meet in distributed shared memory and
