@@ -15,6 +15,9 @@ CASES = [
     ("w8_g128_fp16", 384, 40, "fp16", 8, 128),
     ("w8_g64_bf16_padK", 200, 24, "bf16", 8, 64),
     ("w4_perc_bf16_const_col", 64, 8, "bf16", 4, -1),
+    ("w4_g72_bf16", 216, 40, "bf16", 4, 72),    # group sizes that do not divide the 64-k tile (round 2: per-word look-up)
+    ("w4_g40_fp16_padK", 100, 24, "fp16", 4, 40),
+    ("w4_g32_bf16", 128, 16, "bf16", 4, 32),
 ]
 
 
