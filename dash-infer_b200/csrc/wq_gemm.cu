@@ -14,8 +14,12 @@
 //     lop3/shf only, run C^T[n16 x m8] += W^T[n16 x k16] * A^T[k16 x m8] on the tensor cores
 //     (weights = A operand, activations = B operand: batch 1..8 fills the n8 side, no wasted rows),
 //     and apply the affine dequant on the fp32 accumulators:  s * (acc - (16+z) * sum_k a).
-//   * split-K across CTAs with fp32 partials in the caller's workspace; the last CTA of an n-group
-//     (device counter) sums them in fixed order => deterministic, fused bias/activation/residual.
+//   * split-K across CTAs.  Default: the S in {2, 4, 8} k-slices of a tile form a thread-block cluster, the partial tiles stay
+//     in shared memory and every CTA sums and finishes its share of the tile through distributed shared memory (slice order:
+//     deterministic).  Fallback (narrow shapes, forced splits, the fused all-reduce): fp32 partials in the caller's workspace,
+//     the last CTA of an n-group (device counter) sums them in fixed order.  Either way: fused bias / activation / residual /
+//     SwiGLU, optionally a self-contained RMSNorm prologue (b2_gemm_fuse).
+//   * the 16-bit type of activations / outputs / scales is a template parameter (Ft<H>: bf16 or fp16; fp16 uses 128 + q).
 //
 // Roofline: HBM-bound; algorithmic bytes/launch = K*N*wbits/8 + 4*G*N + 2*M*(K+N).
 #include <cstdio>

@@ -26,6 +26,11 @@
 //                 several units; barriers, TMEM and ring phases carry over and the next unit's first weight stages are
 //                 issued before the epilogue (MULTI instantiation).
 //
+//   variants    : DUAL (two CTAs per SM: half-depth stages, 256 TMEM columns — used where >= 2 units per SM exist without more
+//                 split-K), GROUPED (sub-channel int4: the scale is applied to the weights in the dequant warps; group sizes that
+//                 do not divide the 64-k tile look their params up per 8-k word), A8 (fp8 activations, kind::f8f6f4), H (fp16
+//                 instead of bf16 activations / outputs), the RMSNorm hand-off (row statistics + gamma-scaled copy out, 1/rms in).
+//
 // Roofline: HBM-bound up to M ~ 64 (256 FLOP/B ~ the tensor/HBM ridge); report both.
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
 
