@@ -212,7 +212,8 @@ class DecodeStack:
         # sum x^2 in the same pass and scale their reduced tile by 1/rms — two launches per layer disappear.  Every CTA
         # repeats the normalisation of its k-slice of every live row, so the saving shrinks with the batch: measured on
         # B200 (Qwen2-7B int4, whole step) batch 1: 445 -> 462 tok/s, batch 8: 3241 -> 3140.  Default: batches <= 2.
-        self.norm_self = os.environ.get("B2_NORM_SELF", "1") != "0" and not self.fuse_norm
+        self.norm_self = (os.environ.get("B2_NORM_SELF", "1") != "0" and not self.fuse_norm
+                          and (group == -1 or group % 64 == 0))  # other group sizes run on the tcgen05 kernel at every batch
         self.norm_self_max_b = int(os.environ.get("B2_NORM_SELF_MAX_B", "2"))
         # RMSNorm hand-off between the tcgen05 GEMMs (batches >= 17, TP = 1): o_proj / down_proj also write the next
         # norm's input scaled by its gamma plus per-tile row statistics; qkv / gate+up / lm_head scale their result rows by
