@@ -115,12 +115,14 @@ int b2_gemm_wq_run(b2_gemm_wq_t handle, const void* A, int64_t lda, void* C, int
  * state (o_proj / down_proj with residual) also emits, per 128-channel tile, the sum of squares of each output row
  * (sumsq_out [tiles][M], tiles = b2_gemm_wq_sumsq_parts); the consumer applies LayerNormNoBeta on the fly while staging
  * its activations: a_norm[m,k] = A[m,k] * rsqrt(sum_p norm_sumsq[p][m] / norm_hidden + eps) * gamma[k], rounded to FT
- * exactly like the stand-alone b2_rmsnorm.  Either half may be NULL.  Returns B2_ERR_UNSUPPORTED for M > 16.
+ * exactly like the stand-alone b2_rmsnorm.  Either half may be NULL.  These two forms exist for M <= 16 (B2_ERR_UNSUPPORTED
+ * above; batches >= 17 have the hand-off form described with the struct).
  * Self-contained form (norm_sumsq == NULL, norm_gamma != NULL, norm_hidden == K): the consumer needs nothing from its
  * producer — it stages bf16(A[m,k] * gamma[k]), collects sum_k A[m,k]^2 over its own k-slice in the same pass (the split-K
  * reducer adds the slices), and multiplies the reduced fp32 tile by rsqrt(sum / K + eps) before alpha / bias / activation:
  *   C = act(alpha * inv_rms[m] * sum_k bf16(A[m,k] gamma[k]) W[k,n] + bias)   — one bf16 rounding per activation, like the
- * stand-alone norm, at a different point of the product.  This is the form the decode stack uses at batches <= 16. */
+ * stand-alone norm, at a different point of the product.  Every CTA repeats the normalisation of its k-slice of every live
+ * row, so it pays at tiny batches only: the decode stack uses it at batches <= 2 (FT(x) stands for bf16 or fp16). */
 typedef struct {
   const float* norm_sumsq; /* [norm_parts][M] or NULL */
   const void* norm_gamma;  /* [K] FT */
