@@ -79,8 +79,8 @@ typedef struct {
   int32_t K;
   int32_t N;
   int32_t wbits;      /* 4, 8 or 16 */
-  int32_t group_size; /* -1 per-channel; otherwise a multiple of 64 */
-  int32_t ft;         /* B2_DT_BF16 (activations, scales, zeros, bias, output) */
+  int32_t group_size; /* -1 per-channel; otherwise a multiple of 64 (int4: any multiple of 8 >= 32) */
+  int32_t ft;         /* B2_DT_BF16 or B2_DT_F16 (activations, scales, zeros, bias, residual, output) */
   int32_t qtype;      /* B2_DT_U8 (uint4x2 or uint8) or B2_DT_I8 (wbits 8) */
   int32_t max_m;      /* largest M this handle will be run with (sizes persistent buffers) */
   int32_t reserved;
@@ -169,7 +169,7 @@ size_t b2_gemm_wq_algo_bytes(b2_gemm_wq_t handle, int M);
  * Span tables: device arrays [batch, max_spans_per_seq] of device pointers.
  * ===================================================================================== */
 typedef struct {
-  int32_t ft;                /* B2_DT_BF16 */
+  int32_t ft;                /* B2_DT_BF16 or B2_DT_F16: Q, the output, an unquantized cache (head 64: bf16 only) */
   int32_t quant_mode;        /* B2_KV_NONE / B2_KV_I8 / B2_KV_U4 */
   int32_t n_heads;           /* query heads on this rank */
   int32_t n_groups;          /* kv heads on this rank; n_heads % n_groups == 0, n_heads/n_groups <= 16 */

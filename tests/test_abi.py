@@ -53,3 +53,27 @@ def test_param_validation_without_gpu():
     assert lib.b2_span_bytes(C.byref(cfg)) == 32 * 4 * 64 + 2 * 32 * 4 * 4
     cfg = _lib.SpanCfg(_lib.DT_BF16, 0, 28, 4, 128, 48, 16, 0)  # span 48 invalid (span_cache_config.cpp:32-48)
     assert lib.b2_span_bytes(C.byref(cfg)) == 0
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors in b200spark/_lib.py against the C compiler's view of include/b200spark.h (sizeof / offsetof of
+    every struct that crosses the C ABI by pointer)."""
+    import ctypes as C
+    import subprocess
+    from b200spark import _lib
+    structs = {"b2_gemm_wq_desc": _lib.GemmDesc, "b2_span_cfg": _lib.SpanCfg, "b2_rope_cfg": _lib.RopeCfg, "b2_gemm_fuse": _lib.GemmFuse}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200spark.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append('  printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(out[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(out["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
